@@ -1,0 +1,3 @@
+"""mpcgpu: B200-native batched closed-loop MPC evaluation behind the reference's evaluator API."""
+from .plant import Channels, c2d_fopdt, simulate, cond_min  # noqa: F401
+from .problems import LinearProblem, shell3x3, woodberry, shell7x5, synthetic_population, CASES  # noqa: F401
