@@ -1,0 +1,133 @@
+/*
+ * mpcgpu.h -- C ABI of libmpcgpu.so: batched closed-loop MPC evaluation for controller tuning on B200.
+ *
+ * Drop-in boundary.  Each entry point replaces what a MATLAB caller does today through
+ *   [y,u,t,ys,uopt] = closedloop_toolbox(mpc_toolbox,r,v,N,Nu,delta,lambda,nit)
+ *        /root/reference/MPC-Tuning/MPC_Tuning/closedloop_toolbox.m:1
+ *   [g,h] = GAM_fun(X,Par)            /root/reference/MPC-Tuning/MPC_Tuning/GAM_fun.m:1   (cost mode GAM)
+ *   VNS trial cost                    /root/reference/MPC-Tuning/MPC_Tuning/VNS2.m:147-195 (cost mode VNS)
+ * and is what a MEX gateway binds (mex/mpcgpu_mex.c).
+ *
+ * Conventions: plain C, no exceptions, int return codes (0 = ok), caller-owned buffers, doubles are IEEE
+ * fp64.  A handle owns one CUDA device context + stream and is thread-compatible (one thread at a
+ * time).  There is NO CPU fallback: every call fails with MPCGPU_ERR_CUDA when no device is usable.
+ */
+#ifndef MPCGPU_H
+#define MPCGPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MPCGPU_MAX_NY 8
+#define MPCGPU_MAX_NU 4
+#define MPCGPU_MAX_NW 8   /* nu + nd */
+#define MPCGPU_MAX_P 255  /* nbp <= 8 bits (MPCTuning.m:283) */
+#define MPCGPU_MAX_M 15   /* nbc  = 4 bits (MPCTuning.m:284) */
+
+enum {
+    MPCGPU_OK = 0,
+    MPCGPU_ERR_ARG = 1,      /* bad argument / unsupported size                */
+    MPCGPU_ERR_CUDA = 2,     /* CUDA runtime error, see mpcgpu_last_error()    */
+    MPCGPU_ERR_STATE = 3,    /* call order (e.g. run before upload)            */
+    MPCGPU_ERR_UNSUPPORTED = 4
+};
+
+/* per-candidate status codes (status[] output) */
+enum {
+    MPCGPU_CAND_OK = 0,
+    MPCGPU_CAND_INFEASIBLE = 1,   /* QP infeasible (cannot happen with MV box + rate limits only) */
+    MPCGPU_CAND_ITER_CAP = 2,     /* active-set iteration cap hit                                 */
+    MPCGPU_CAND_NOT_PD = 3,       /* Hessian not positive definite (lambda == 0 and rank-deficient G) */
+    MPCGPU_CAND_INVALID = 4       /* horizons illegal: PreCon.m:23 / VNS2.m:135 (only if check_valid) */
+};
+
+/* cost modes */
+enum {
+    MPCGPU_COST_RAW = 0,  /* trajectories only: closedloop_toolbox.m outputs                      */
+    MPCGPU_COST_GAM = 1,  /* g_i = sum_k (y_i - Yref_i)^2, n x ny           (GAM_fun.m:110-115)   */
+    MPCGPU_COST_VNS = 2   /* F = sum(j21+j22) + N + sum(Jnu), n             (VNS2.m:147-195)      */
+};
+
+/* The state `Par` carries into the objective functions (MPCTuning.m:307-340) for a LINEAR plant whose
+ * channels are first-order-plus-dead-time, already L/R-scaled (MPCTuning.m:154-200):
+ *    y_ij(k) = a*y_ij(k-1) + b0*w_j(k-d) + b1*w_j(k-d-1),   w = [MVs ; MDs]
+ * All matrices are row-major ny x (nu+nd).  Bounds may be +-INFINITY. */
+typedef struct {
+    int32_t ny, nu, nd, nit;
+    int32_t pmax, mmax;            /* 2^nbp - 1, 2^nbc - 1 (MPCTuning.m:283-284)                  */
+    int32_t inK;                   /* 1-based first cost sample of the VNS objective (VNS2.m:43)  */
+    int32_t reserved;
+    const double *a, *b0, *b1;
+    const int32_t *d;
+    const double *umin, *umax, *dumin, *dumax;       /* nu : MV(i).Min/Max/RateMin/RateMax        */
+    const double *ymin, *ymax, *ecr_min, *ecr_max;   /* ny : OV(i).Min/Max/MinECR/MaxECR          */
+    const double *su, *sy;                           /* MV / OV ScaleFactor                       */
+    double rho_ecr;                                  /* Weights.ECR                               */
+    const double *r;       /* nit x ny, time-major: set-point (Par.Xsp')                          */
+    const double *v;       /* nit x nd, time-major: measured disturbance (Par.mdv'), may be NULL  */
+    const double *yref;    /* ny x nit: reference trajectory (Par.Yref)                           */
+    const int32_t *dmin;   /* ny: per-output minimum dead time (MPCTuning.m:257-262)              */
+} mpcgpu_problem;
+
+typedef struct mpcgpu_handle mpcgpu_handle;
+
+typedef struct {
+    uint64_t candidates;        /* candidates evaluated since create                       */
+    uint64_t closed_loops;      /* closed-loop simulations (VNS on a square plant: ny each) */
+    uint64_t qp_solves;         /* closed_loops * nit + open-loop QPs                      */
+    uint64_t qp_constrained;    /* QPs that left the unconstrained fast path               */
+    uint64_t as_iterations;     /* active-set iterations (adds + drops)                    */
+    uint64_t kernel_launches;   /* CUDA kernels launched by this handle                    */
+    double last_build_ms;       /* device time of the prediction/Hessian builder kernel(s) */
+    double last_sim_ms;         /* device time of the closed-loop kernel(s) (dominant)     */
+    double last_total_ms;       /* device time of the whole last run                       */
+} mpcgpu_counters;
+
+/* Create an evaluator on CUDA device `device` (-1: current).  Copies the problem, builds the
+ * candidate-independent prediction tables (step responses, prefix Grams, free-response maps). */
+int mpcgpu_create(const mpcgpu_problem *problem, int device, mpcgpu_handle **out);
+void mpcgpu_destroy(mpcgpu_handle *h);
+
+/* Replace the signals (closedloop_toolbox takes r, v, nit per call: closedloop_toolbox.m:1).
+ * r: nit x ny, v: nit x nd (may be NULL when nd == 0), yref: ny x nit (may be NULL -> zeros). */
+int mpcgpu_set_signals(mpcgpu_handle *h, int nit, const double *r, const double *v, const double *yref);
+
+/* One call = one population.  HOST pointers; copies in, runs, copies out, synchronises.
+ *   N, Nu   : n            prediction / control horizon per candidate (max(N), max(Nu) of the caller)
+ *   delta   : n x ny       row-major (candidate-major)   Weights.OV
+ *   lambda  : n x nu       row-major                     Weights.MVRate
+ *   cost    : GAM: n x ny ; VNS: n ; RAW: ignored (may be NULL)
+ *   y,u,ys,uopt : NULL or n x (ny|nu) x nit, signals x time per candidate (closedloop_toolbox.m:103-107)
+ *   status  : NULL or n
+ * Failed candidates get NaN cost and a non-zero status; the call itself still returns MPCGPU_OK, which
+ * is what lets the reference's try/catch callers (GAM_fun.m:80-91, VNS2.m:151-163) keep working. */
+int mpcgpu_eval_batch(mpcgpu_handle *h, int n, const int32_t *N, const int32_t *Nu, const double *delta,
+                      const double *lambda, int cost_mode, double *cost, double *y, double *u, double *ys,
+                      double *uopt, int32_t *status);
+
+/* Split form of the same call, for callers that keep a population resident on the device:
+ * upload (H2D + host-side size bucketing) -> run (kernels only, asynchronous on `stream`) -> download. */
+int mpcgpu_upload(mpcgpu_handle *h, int n, const int32_t *N, const int32_t *Nu, const double *delta,
+                  const double *lambda);
+int mpcgpu_run(mpcgpu_handle *h, int cost_mode, int want_traj, void *cuda_stream /* cudaStream_t or NULL */);
+int mpcgpu_download(mpcgpu_handle *h, int cost_mode, double *cost, double *y, double *u, double *ys,
+                    double *uopt, int32_t *status);
+/* Device pointer of the cost buffer of the last run (n x ny or n doubles), for on-device consumers
+ * such as an NCCL all-gather of fitness. */
+int mpcgpu_cost_device_ptr(mpcgpu_handle *h, int cost_mode, void **ptr, int *count);
+
+int mpcgpu_get_counters(mpcgpu_handle *h, mpcgpu_counters *out);
+const char *mpcgpu_last_error(mpcgpu_handle *h); /* h may be NULL: last create() error */
+int mpcgpu_device_count(void);
+
+/* fp64 FMA throughput microbenchmark (TFLOP/s, 2 flops per FMA) used as the roofline denominator of
+ * this path (MEASURED_PEAKS.json has no fp64 entry). */
+int mpcgpu_measure_fp64_peak(int device, double *tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPCGPU_H */

@@ -1,0 +1,19 @@
+// mpc_tables.h -- host-side problem ingest: layout + candidate-independent prediction tables.
+#pragma once
+#include <string>
+#include <vector>
+
+#include "../../include/mpcgpu.h"
+#include "mpc_layout.h"
+
+struct MpcHostTables {
+    MpcLayout L;
+    std::vector<double> TG, TK, S1;
+    std::vector<double> step;  // s_ij(n), [i][j][n], n = 0..pmax+mmax
+    std::vector<double> r, v, yref;
+    std::vector<int> dmin;
+};
+
+// Returns empty string on success, otherwise an error message.
+std::string mpc_build_tables(const mpcgpu_problem &pb, MpcHostTables &out);
+std::string mpc_set_signals(MpcHostTables &t, int nit, const double *r, const double *v, const double *yref);

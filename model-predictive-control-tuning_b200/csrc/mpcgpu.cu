@@ -1,0 +1,547 @@
+// mpcgpu.cu -- kernels + C ABI of libmpcgpu.so (include/mpcgpu.h).  sm_100a only, no CPU fallback.
+//
+// Launch structure of one population evaluation (mpcgpu_run):
+//   candidates are bucketed on the host by control horizon m (the only size that fixes the shared-memory
+//   footprint nz = nu*m), largest m first, each bucket on its own forked stream:
+//     k_build : one CTA (128 threads) per candidate  -> M (nst x nz), W = H^-1 (nz x nz) in HBM
+//     k_sim   : one warp per closed-loop run; M staged into shared memory once,
+//               W read through L1/L2 only when a QP leaves the unconstrained fast path
+//   k_finish  : VNS only, F = sum_runs partial + N
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/mpcgpu.h"
+#include "mpc_core.cuh"
+#include "mpc_tables.h"
+
+#define NSTREAM 4
+#define BUILD_THREADS 128
+
+static std::string g_create_error;
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            char b_[512];                                                                          \
+            snprintf(b_, sizeof(b_), "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+            h->err = b_;                                                                           \
+            return MPCGPU_ERR_CUDA;                                                                \
+        }                                                                                          \
+    } while (0)
+
+struct DevCand {
+    const int *N, *Nu;
+    const double *delta, *lambda;
+    const long long *offM, *offW;
+    double *M, *W;
+    int *bstatus;  // builder status per candidate
+};
+
+struct DevOut {
+    double *cost;   // GAM: n*ny ; VNS: n
+    double *part;   // VNS partial sums n*runs
+    int *status;    // n
+    unsigned long long *counters;  // [0] constrained QPs [1] active-set iterations
+    double *y, *u, *ys, *uopt;     // optional trajectories
+};
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(BUILD_THREADS) k_build(const MpcLayout L, const MpcTables T, const int *order,
+                                                         int count, DevCand C) {
+    extern __shared__ double smem_b[];
+    __shared__ int flag;
+    const int item = blockIdx.x;
+    if (item >= count) return;
+    const int c = order[item];
+    const int p = C.N[c], m = C.Nu[c];
+    const int st = mpc_build_candidate(L, T, p, m, C.delta + (size_t)c * L.ny, C.lambda + (size_t)c * L.nu, smem_b,
+                                       C.M + C.offM[c], C.W + C.offW[c], &flag);
+    if (threadIdx.x == 0) C.bstatus[c] = st;
+}
+
+// One warp per (candidate, run).  mode: 0 RAW, 1 GAM, 2 VNS.
+__global__ void __launch_bounds__(32) k_sim(const MpcLayout L, const MpcTables T, const int *order, int count, int runs,
+                                            int mode, int square, DevCand C, DevOut O) {
+    extern __shared__ double smem_s[];
+    const int item = blockIdx.x;
+    if (item >= count * runs) return;
+    const int c = order[item / runs];
+    const int run = item - (item / runs) * runs;
+    const int p = C.N[c], m = C.Nu[c];
+    const int ny = L.ny, nu = L.nu, nit = L.nit;
+    if (C.bstatus[c] != 0) {
+        if ((threadIdx.x & 31) == 0) {
+            atomicMax(O.status + c, C.bstatus[c]);
+            if (mode == 1) for (int i = 0; i < ny; ++i) O.cost[(size_t)c * ny + i] = NAN;
+            if (mode == 2) O.part[(size_t)c * runs + run] = NAN;
+        }
+        return;
+    }
+    MpcRunOut out;
+    out.cost = mode == 1 ? O.cost + (size_t)c * ny : (mode == 2 ? O.part + (size_t)c * runs + run : nullptr);
+    out.y = O.y ? O.y + (size_t)c * ny * nit : nullptr;
+    out.u = O.u ? O.u + (size_t)c * nu * nit : nullptr;
+    out.ys = O.ys ? O.ys + (size_t)c * ny * nit : nullptr;
+    out.uopt = O.uopt ? O.uopt + (size_t)c * nu * nit : nullptr;
+    out.counters = O.counters;
+    const int sel = mode == 2 ? (square ? run : -1) : -2;
+    const int st = mpc_sim_run(L, T, p, m, C.M + C.offM[c], C.W + C.offW[c], mode, sel, smem_s, out);
+    if (st != 0 && (threadIdx.x & 31) == 0) atomicMax(O.status + c, st);
+}
+
+__global__ void k_finish_vns(int n, int runs, const int *N, const double *part, const int *status, double *cost) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    double acc = 0.0;
+    for (int r = 0; r < runs; ++r) acc += part[(size_t)c * runs + r];  // fixed order: deterministic
+    cost[c] = status[c] ? NAN : acc + (double)N[c];
+}
+
+__global__ void k_mark_invalid(int n, const int *invalid, int ny, int mode, int *status, double *cost) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n || !invalid[c]) return;
+    status[c] = MPCGPU_CAND_INVALID;
+    if (mode == 1) for (int i = 0; i < ny; ++i) cost[(size_t)c * ny + i] = NAN;
+    if (mode == 2) cost[c] = NAN;
+}
+
+// fp64 FMA peak: 8 independent chains per thread
+__global__ void k_fp64_peak(double *out, int iters) {
+    double a0 = threadIdx.x * 1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double b = 1.0000001, c = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+        a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+// ------------------------------------------------------------------------------------------------
+template <typename Tp>
+struct DBuf {
+    Tp *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = n + n / 4 + 16;
+        cudaError_t e = cudaMalloc((void **)&p, want * sizeof(Tp));
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+template <typename Tp>
+struct HBuf {  // pinned host staging
+    Tp *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        size_t want = n + n / 4 + 16;
+        cudaError_t e = cudaMallocHost((void **)&p, want * sizeof(Tp));
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+struct mpcgpu_handle {
+    int device = 0;
+    std::string err;
+    MpcHostTables ht;
+    cudaStream_t stream = nullptr;          // own stream for eval_batch / upload / download
+    cudaStream_t pool[NSTREAM] = {};
+    cudaEvent_t ev_fork = nullptr, ev_join[NSTREAM] = {}, ev_t0 = nullptr, ev_t1 = nullptr, ev_t2 = nullptr;
+    DBuf<double> dTG, dTK, dS1, dR, dV, dYref;
+    // population
+    int n = 0;
+    bool uploaded = false, ran = false;
+    int last_mode = -1, last_traj = 0;
+    std::vector<int> hN, hNu, hOrder, hInvalid;
+    std::vector<long long> hOffM, hOffW;
+    struct Bucket { int m, off, count; };
+    std::vector<Bucket> buckets;
+    int n_valid = 0;
+    DBuf<int> dN, dNu, dOrder, dInvalid, dBStatus, dStatus;
+    DBuf<long long> dOffM, dOffW;
+    DBuf<double> dDelta, dLambda, dM, dW, dCost, dPart, dY, dU, dYs, dUopt;
+    DBuf<unsigned long long> dCounters;
+    HBuf<double> pinD, pinOut;
+    HBuf<int> pinI;
+    mpcgpu_counters cnt = {};
+    size_t smem_optin = 0;
+};
+
+static MpcTables dev_tables(mpcgpu_handle *h) {
+    MpcTables T;
+    T.TG = h->dTG.p; T.TK = h->dTK.p; T.S1 = h->dS1.p; T.r = h->dR.p; T.v = h->dV.p; T.yref = h->dYref.p;
+    return T;
+}
+
+static int upload_signals(mpcgpu_handle *h) {
+    const MpcHostTables &t = h->ht;
+    CK(h->dR.ensure(t.r.size()));
+    CK(h->dV.ensure(t.v.size()));
+    CK(h->dYref.ensure(t.yref.size()));
+    CK(cudaMemcpyAsync(h->dR.p, t.r.data(), t.r.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->dV.p, t.v.data(), t.v.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->dYref.p, t.yref.data(), t.yref.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return MPCGPU_OK;
+}
+
+extern "C" int mpcgpu_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+extern "C" const char *mpcgpu_last_error(mpcgpu_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+extern "C" int mpcgpu_create(const mpcgpu_problem *problem, int device, mpcgpu_handle **out) {
+    if (!problem || !out) { g_create_error = "NULL argument"; return MPCGPU_ERR_ARG; }
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0) {
+        g_create_error = std::string("no CUDA device: ") + cudaGetErrorString(ce) + " (mpcgpu has no CPU fallback)";
+        return MPCGPU_ERR_CUDA;
+    }
+    mpcgpu_handle *h = new mpcgpu_handle();
+    if (device < 0) cudaGetDevice(&device);
+    h->device = device;
+    std::string e = mpc_build_tables(*problem, h->ht);
+    if (!e.empty()) { g_create_error = e; delete h; return MPCGPU_ERR_ARG; }
+    auto fail = [&](const char *what, cudaError_t ce2) {
+        g_create_error = std::string(what) + ": " + cudaGetErrorString(ce2);
+        mpcgpu_destroy(h);
+        return MPCGPU_ERR_CUDA;
+    };
+    if ((ce = cudaSetDevice(device)) != cudaSuccess) return fail("cudaSetDevice", ce);
+    cudaDeviceProp prop;
+    if ((ce = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return fail("cudaGetDeviceProperties", ce);
+    if (prop.major < 10) {
+        g_create_error = "mpcgpu is built for sm_100a (B200) only; found compute capability " + std::to_string(prop.major) +
+                         "." + std::to_string(prop.minor);
+        mpcgpu_destroy(h);
+        return MPCGPU_ERR_CUDA;
+    }
+    h->smem_optin = prop.sharedMemPerBlockOptin;
+    if ((ce = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("stream", ce);
+    for (int i = 0; i < NSTREAM; ++i) {
+        if ((ce = cudaStreamCreateWithFlags(&h->pool[i], cudaStreamNonBlocking)) != cudaSuccess) return fail("stream", ce);
+        if ((ce = cudaEventCreateWithFlags(&h->ev_join[i], cudaEventDisableTiming)) != cudaSuccess) return fail("event", ce);
+    }
+    if ((ce = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming)) != cudaSuccess) return fail("event", ce);
+    if ((ce = cudaEventCreate(&h->ev_t0)) != cudaSuccess) return fail("event", ce);
+    if ((ce = cudaEventCreate(&h->ev_t1)) != cudaSuccess) return fail("event", ce);
+    if ((ce = cudaEventCreate(&h->ev_t2)) != cudaSuccess) return fail("event", ce);
+    const MpcHostTables &t = h->ht;
+    if ((ce = h->dTG.ensure(t.TG.size())) != cudaSuccess) return fail("alloc TG", ce);
+    if ((ce = h->dTK.ensure(t.TK.size())) != cudaSuccess) return fail("alloc TK", ce);
+    if ((ce = h->dS1.ensure(t.S1.size())) != cudaSuccess) return fail("alloc S1", ce);
+    cudaMemcpy(h->dTG.p, t.TG.data(), t.TG.size() * sizeof(double), cudaMemcpyHostToDevice);
+    cudaMemcpy(h->dTK.p, t.TK.data(), t.TK.size() * sizeof(double), cudaMemcpyHostToDevice);
+    ce = cudaMemcpy(h->dS1.p, t.S1.data(), t.S1.size() * sizeof(double), cudaMemcpyHostToDevice);
+    if (ce != cudaSuccess) return fail("copy tables", ce);
+    if (upload_signals(h) != MPCGPU_OK) { g_create_error = h->err; mpcgpu_destroy(h); return MPCGPU_ERR_CUDA; }
+    if ((ce = h->dCounters.ensure(4)) != cudaSuccess) return fail("alloc counters", ce);
+    // allow large dynamic shared memory on both kernels
+    cudaFuncSetAttribute(k_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin);
+    cudaFuncSetAttribute(k_sim, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin);
+    // check the largest footprints fit
+    const size_t sb = mpc_builder_smem_doubles(t.L.nu * t.L.mmax, t.L.nst) * sizeof(double);
+    const size_t ss = mpc_sim_smem_doubles(t.L, t.L.mmax) * sizeof(double);
+    if (sb > h->smem_optin || ss > h->smem_optin) {
+        g_create_error = "problem too large for shared memory (builder " + std::to_string(sb) + " B, sim " +
+                         std::to_string(ss) + " B)";
+        mpcgpu_destroy(h);
+        return MPCGPU_ERR_UNSUPPORTED;
+    }
+    if (t.L.has_ov_bounds) {
+        g_create_error = "finite OV bounds (soft output constraints) are not supported by this build";
+        mpcgpu_destroy(h);
+        return MPCGPU_ERR_UNSUPPORTED;
+    }
+    *out = h;
+    return MPCGPU_OK;
+}
+
+extern "C" void mpcgpu_destroy(mpcgpu_handle *h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    h->dTG.release(); h->dTK.release(); h->dS1.release(); h->dR.release(); h->dV.release(); h->dYref.release();
+    h->dN.release(); h->dNu.release(); h->dOrder.release(); h->dInvalid.release(); h->dBStatus.release();
+    h->dStatus.release(); h->dOffM.release(); h->dOffW.release(); h->dDelta.release(); h->dLambda.release();
+    h->dM.release(); h->dW.release(); h->dCost.release(); h->dPart.release(); h->dY.release(); h->dU.release();
+    h->dYs.release(); h->dUopt.release(); h->dCounters.release();
+    h->pinD.release(); h->pinOut.release(); h->pinI.release();
+    for (int i = 0; i < NSTREAM; ++i) {
+        if (h->pool[i]) cudaStreamDestroy(h->pool[i]);
+        if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]);
+    }
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_t0) cudaEventDestroy(h->ev_t0);
+    if (h->ev_t1) cudaEventDestroy(h->ev_t1);
+    if (h->ev_t2) cudaEventDestroy(h->ev_t2);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+extern "C" int mpcgpu_set_signals(mpcgpu_handle *h, int nit, const double *r, const double *v, const double *yref) {
+    if (!h) return MPCGPU_ERR_ARG;
+    CK(cudaSetDevice(h->device));
+    std::string e = mpc_set_signals(h->ht, nit, r, v, yref);
+    if (!e.empty()) { h->err = e; return MPCGPU_ERR_ARG; }
+    return upload_signals(h);
+}
+
+extern "C" int mpcgpu_upload(mpcgpu_handle *h, int n, const int32_t *N, const int32_t *Nu, const double *delta,
+                             const double *lambda) {
+    if (!h) return MPCGPU_ERR_ARG;
+    if (n < 0 || (n > 0 && (!N || !Nu || !delta || !lambda))) { h->err = "bad population arguments"; return MPCGPU_ERR_ARG; }
+    CK(cudaSetDevice(h->device));
+    const MpcLayout &L = h->ht.L;
+    const int ny = L.ny, nu = L.nu;
+    h->n = n; h->uploaded = false; h->ran = false;
+    h->hN.assign(N, N + n); h->hNu.assign(Nu, Nu + n);
+    h->hInvalid.assign(n, 0);
+    h->hOffM.assign(n, 0); h->hOffW.assign(n, 0);
+    // bucket by m, largest first; illegal horizons never reach a kernel
+    std::vector<std::vector<int>> by_m(L.mmax + 1);
+    long long offM = 0, offW = 0;
+    h->n_valid = 0;
+    for (int c = 0; c < n; ++c) {
+        const int p = N[c], m = Nu[c];
+        if (p < 2 || p > L.pmax || m < 1 || m > L.mmax || m >= p) { h->hInvalid[c] = 1; continue; }
+        by_m[m].push_back(c);
+        const long long nz = (long long)nu * m;
+        h->hOffM[c] = offM; offM += (long long)L.nst * nz;
+        h->hOffW[c] = offW; offW += nz * nz;
+        h->n_valid++;
+    }
+    h->hOrder.clear(); h->buckets.clear();
+    for (int m = L.mmax; m >= 1; --m) {
+        if (by_m[m].empty()) continue;
+        mpcgpu_handle::Bucket b{m, (int)h->hOrder.size(), (int)by_m[m].size()};
+        h->hOrder.insert(h->hOrder.end(), by_m[m].begin(), by_m[m].end());
+        h->buckets.push_back(b);
+    }
+    const size_t nn = (size_t)(n > 0 ? n : 1);
+    CK(h->dN.ensure(nn)); CK(h->dNu.ensure(nn)); CK(h->dOrder.ensure(nn)); CK(h->dInvalid.ensure(nn));
+    CK(h->dBStatus.ensure(nn)); CK(h->dStatus.ensure(nn)); CK(h->dOffM.ensure(nn)); CK(h->dOffW.ensure(nn));
+    CK(h->dDelta.ensure(nn * ny)); CK(h->dLambda.ensure(nn * nu));
+    CK(h->dM.ensure((size_t)offM + 1)); CK(h->dW.ensure((size_t)offW + 1));
+    // stage through pinned memory: [delta | lambda] doubles, [N | Nu | order | invalid] ints, offsets
+    CK(h->pinD.ensure(nn * (ny + nu) + 2 * nn));
+    CK(h->pinI.ensure(4 * nn));
+    std::memcpy(h->pinD.p, delta, sizeof(double) * (size_t)n * ny);
+    std::memcpy(h->pinD.p + (size_t)n * ny, lambda, sizeof(double) * (size_t)n * nu);
+    long long *poff = reinterpret_cast<long long *>(h->pinD.p + (size_t)n * (ny + nu));
+    std::memcpy(poff, h->hOffM.data(), sizeof(long long) * n);
+    std::memcpy(poff + n, h->hOffW.data(), sizeof(long long) * n);
+    std::memcpy(h->pinI.p, N, sizeof(int) * n);
+    std::memcpy(h->pinI.p + n, Nu, sizeof(int) * n);
+    std::memcpy(h->pinI.p + 2 * (size_t)n, h->hOrder.data(), sizeof(int) * h->hOrder.size());
+    std::memcpy(h->pinI.p + 3 * (size_t)n, h->hInvalid.data(), sizeof(int) * n);
+    cudaStream_t s = h->stream;
+    if (n > 0) {
+        CK(cudaMemcpyAsync(h->dDelta.p, h->pinD.p, sizeof(double) * (size_t)n * ny, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(h->dLambda.p, h->pinD.p + (size_t)n * ny, sizeof(double) * (size_t)n * nu, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(h->dOffM.p, poff, sizeof(long long) * n, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(h->dOffW.p, poff + n, sizeof(long long) * n, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(h->dN.p, h->pinI.p, sizeof(int) * n, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(h->dNu.p, h->pinI.p + n, sizeof(int) * n, cudaMemcpyHostToDevice, s));
+        if (!h->hOrder.empty())
+            CK(cudaMemcpyAsync(h->dOrder.p, h->pinI.p + 2 * (size_t)n, sizeof(int) * h->hOrder.size(), cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(h->dInvalid.p, h->pinI.p + 3 * (size_t)n, sizeof(int) * n, cudaMemcpyHostToDevice, s));
+    }
+    CK(cudaStreamSynchronize(s));  // pinned staging is reused by the next upload
+    h->uploaded = true;
+    return MPCGPU_OK;
+}
+
+extern "C" int mpcgpu_run(mpcgpu_handle *h, int cost_mode, int want_traj, void *cuda_stream) {
+    if (!h) return MPCGPU_ERR_ARG;
+    if (!h->uploaded) { h->err = "mpcgpu_run before mpcgpu_upload"; return MPCGPU_ERR_STATE; }
+    if (cost_mode < 0 || cost_mode > 2) { h->err = "bad cost_mode"; return MPCGPU_ERR_ARG; }
+    CK(cudaSetDevice(h->device));
+    const MpcLayout &L = h->ht.L;
+    const int n = h->n, ny = L.ny, nu = L.nu, nit = L.nit;
+    cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
+    const int square = (ny == nu) ? 1 : 0;
+    const int runs = (cost_mode == MPCGPU_COST_VNS && square) ? ny : 1;
+    if (cost_mode == MPCGPU_COST_RAW) want_traj = 1;
+    const size_t nn = (size_t)(n > 0 ? n : 1);
+    CK(h->dCost.ensure(nn * ny));
+    CK(h->dPart.ensure(nn * runs));
+    if (want_traj) {
+        CK(h->dY.ensure(nn * ny * nit)); CK(h->dYs.ensure(nn * ny * nit));
+        CK(h->dU.ensure(nn * nu * nit)); CK(h->dUopt.ensure(nn * nu * nit));
+    }
+    DevCand C{h->dN.p, h->dNu.p, h->dDelta.p, h->dLambda.p, h->dOffM.p, h->dOffW.p, h->dM.p, h->dW.p, h->dBStatus.p};
+    DevOut O{h->dCost.p, h->dPart.p, h->dStatus.p, h->dCounters.p,
+             want_traj ? h->dY.p : nullptr, want_traj ? h->dU.p : nullptr, want_traj ? h->dYs.p : nullptr,
+             want_traj ? h->dUopt.p : nullptr};
+    const MpcTables T = dev_tables(h);
+    CK(cudaEventRecord(h->ev_t0, s));
+    CK(cudaMemsetAsync(h->dStatus.p, 0, sizeof(int) * nn, s));
+    CK(cudaMemsetAsync(h->dCounters.p, 0, sizeof(unsigned long long) * 4, s));
+    if (want_traj) {  // rows a run does not own (VNS on a square plant) and invalid candidates read as zero
+        CK(cudaMemsetAsync(h->dY.p, 0, sizeof(double) * nn * ny * nit, s));
+        CK(cudaMemsetAsync(h->dYs.p, 0, sizeof(double) * nn * ny * nit, s));
+        CK(cudaMemsetAsync(h->dU.p, 0, sizeof(double) * nn * nu * nit, s));
+        CK(cudaMemsetAsync(h->dUopt.p, 0, sizeof(double) * nn * nu * nit, s));
+    }
+    uint64_t launches = 0;
+    // ---- phase 1: builders, forked over the stream pool ----
+    const int nb = (int)h->buckets.size();
+    const int nfork = nb < NSTREAM ? nb : NSTREAM;
+    CK(cudaEventRecord(h->ev_fork, s));
+    for (int i = 0; i < nfork; ++i) CK(cudaStreamWaitEvent(h->pool[i], h->ev_fork, 0));
+    for (int b = 0; b < nb; ++b) {
+        const auto &bk = h->buckets[b];
+        const size_t smem = mpc_builder_smem_doubles(nu * bk.m, L.nst) * sizeof(double);
+        k_build<<<bk.count, BUILD_THREADS, smem, h->pool[b % NSTREAM]>>>(L, T, h->dOrder.p + bk.off, bk.count, C);
+        launches++;
+    }
+    for (int i = 0; i < nfork; ++i) {
+        CK(cudaEventRecord(h->ev_join[i], h->pool[i]));
+        CK(cudaStreamWaitEvent(s, h->ev_join[i], 0));
+    }
+    CK(cudaEventRecord(h->ev_t1, s));
+    // ---- phase 2: closed loops ----
+    CK(cudaEventRecord(h->ev_fork, s));
+    for (int i = 0; i < nfork; ++i) CK(cudaStreamWaitEvent(h->pool[i], h->ev_fork, 0));
+    for (int b = 0; b < nb; ++b) {
+        const auto &bk = h->buckets[b];
+        const size_t smem = mpc_sim_smem_doubles(L, bk.m) * sizeof(double);
+        k_sim<<<bk.count * runs, 32, smem, h->pool[b % NSTREAM]>>>(L, T, h->dOrder.p + bk.off, bk.count, runs, cost_mode,
+                                                                  square, C, O);
+        launches++;
+    }
+    for (int i = 0; i < nfork; ++i) {
+        CK(cudaEventRecord(h->ev_join[i], h->pool[i]));
+        CK(cudaStreamWaitEvent(s, h->ev_join[i], 0));
+    }
+    if (cost_mode == MPCGPU_COST_VNS && n > 0) {
+        k_finish_vns<<<(n + 127) / 128, 128, 0, s>>>(n, runs, h->dN.p, h->dPart.p, h->dStatus.p, h->dCost.p);
+        launches++;
+    }
+    if (h->n_valid < n && n > 0) {
+        k_mark_invalid<<<(n + 127) / 128, 128, 0, s>>>(n, h->dInvalid.p, ny, cost_mode, h->dStatus.p, h->dCost.p);
+        launches++;
+    }
+    CK(cudaEventRecord(h->ev_t2, s));
+    CK(cudaGetLastError());
+    h->ran = true; h->last_mode = cost_mode; h->last_traj = want_traj;
+    h->cnt.kernel_launches += launches;
+    h->cnt.candidates += (uint64_t)h->n_valid;
+    h->cnt.closed_loops += (uint64_t)h->n_valid * runs;
+    const uint64_t ol = (cost_mode != MPCGPU_COST_GAM || want_traj) ? 1 : 0;
+    h->cnt.qp_solves += (uint64_t)h->n_valid * runs * ((uint64_t)nit + ol);
+    return MPCGPU_OK;
+}
+
+extern "C" int mpcgpu_download(mpcgpu_handle *h, int cost_mode, double *cost, double *y, double *u, double *ys,
+                               double *uopt, int32_t *status) {
+    if (!h) return MPCGPU_ERR_ARG;
+    if (!h->ran || cost_mode != h->last_mode) { h->err = "mpcgpu_download without a matching mpcgpu_run"; return MPCGPU_ERR_STATE; }
+    if ((y || u || ys || uopt) && !h->last_traj) { h->err = "trajectories were not requested in mpcgpu_run"; return MPCGPU_ERR_STATE; }
+    CK(cudaSetDevice(h->device));
+    const MpcLayout &L = h->ht.L;
+    const int n = h->n, ny = L.ny, nu = L.nu, nit = L.nit;
+    cudaStream_t s = h->stream;
+    // order the copies after the run even when it was issued on a caller stream
+    CK(cudaStreamWaitEvent(s, h->ev_t2, 0));
+    const size_t ncost = cost_mode == MPCGPU_COST_GAM ? (size_t)n * ny : (cost_mode == MPCGPU_COST_VNS ? (size_t)n : 0);
+    CK(h->pinOut.ensure(ncost + 8));
+    CK(h->pinI.ensure(4 * (size_t)(n > 0 ? n : 1)));
+    unsigned long long *pc = reinterpret_cast<unsigned long long *>(h->pinOut.p + ncost);
+    if (cost && ncost) CK(cudaMemcpyAsync(h->pinOut.p, h->dCost.p, sizeof(double) * ncost, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(pc, h->dCounters.p, sizeof(unsigned long long) * 2, cudaMemcpyDeviceToHost, s));
+    if (status && n) CK(cudaMemcpyAsync(h->pinI.p, h->dStatus.p, sizeof(int) * n, cudaMemcpyDeviceToHost, s));
+    if (y) CK(cudaMemcpyAsync(y, h->dY.p, sizeof(double) * (size_t)n * ny * nit, cudaMemcpyDeviceToHost, s));
+    if (ys) CK(cudaMemcpyAsync(ys, h->dYs.p, sizeof(double) * (size_t)n * ny * nit, cudaMemcpyDeviceToHost, s));
+    if (u) CK(cudaMemcpyAsync(u, h->dU.p, sizeof(double) * (size_t)n * nu * nit, cudaMemcpyDeviceToHost, s));
+    if (uopt) CK(cudaMemcpyAsync(uopt, h->dUopt.p, sizeof(double) * (size_t)n * nu * nit, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (cost && ncost) std::memcpy(cost, h->pinOut.p, sizeof(double) * ncost);
+    if (status && n) std::memcpy(status, h->pinI.p, sizeof(int) * n);
+    h->cnt.qp_constrained += pc[0];
+    h->cnt.as_iterations += pc[1];
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, h->ev_t0, h->ev_t1) == cudaSuccess) h->cnt.last_build_ms = ms;
+    if (cudaEventElapsedTime(&ms, h->ev_t1, h->ev_t2) == cudaSuccess) h->cnt.last_sim_ms = ms;
+    if (cudaEventElapsedTime(&ms, h->ev_t0, h->ev_t2) == cudaSuccess) h->cnt.last_total_ms = ms;
+    return MPCGPU_OK;
+}
+
+extern "C" int mpcgpu_eval_batch(mpcgpu_handle *h, int n, const int32_t *N, const int32_t *Nu, const double *delta,
+                                 const double *lambda, int cost_mode, double *cost, double *y, double *u, double *ys,
+                                 double *uopt, int32_t *status) {
+    if (!h) return MPCGPU_ERR_ARG;
+    int rc = mpcgpu_upload(h, n, N, Nu, delta, lambda);
+    if (rc) return rc;
+    const int want_traj = (y || u || ys || uopt) ? 1 : 0;
+    rc = mpcgpu_run(h, cost_mode, want_traj, nullptr);
+    if (rc) return rc;
+    return mpcgpu_download(h, cost_mode, cost, y, u, ys, uopt, status);
+}
+
+extern "C" int mpcgpu_cost_device_ptr(mpcgpu_handle *h, int cost_mode, void **ptr, int *count) {
+    if (!h || !ptr || !count) return MPCGPU_ERR_ARG;
+    if (!h->ran || cost_mode != h->last_mode) { h->err = "no matching run"; return MPCGPU_ERR_STATE; }
+    *ptr = h->dCost.p;
+    *count = cost_mode == MPCGPU_COST_GAM ? h->n * h->ht.L.ny : h->n;
+    return MPCGPU_OK;
+}
+
+extern "C" int mpcgpu_get_counters(mpcgpu_handle *h, mpcgpu_counters *out) {
+    if (!h || !out) return MPCGPU_ERR_ARG;
+    *out = h->cnt;
+    return MPCGPU_OK;
+}
+
+extern "C" int mpcgpu_measure_fp64_peak(int device, double *tflops) {
+    if (!tflops) return MPCGPU_ERR_ARG;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return MPCGPU_ERR_CUDA;
+    if (device >= 0 && cudaSetDevice(device) != cudaSuccess) return MPCGPU_ERR_CUDA;
+    cudaDeviceProp prop;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return MPCGPU_ERR_CUDA;
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 16;
+    double *d = nullptr;
+    if (cudaMalloc((void **)&d, sizeof(double) * blocks * threads) != cudaSuccess) return MPCGPU_ERR_CUDA;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(a);
+        k_fp64_peak<<<blocks, threads>>>(d, iters);
+        cudaEventRecord(b);
+        if (cudaEventSynchronize(b) != cudaSuccess) { cudaFree(d); return MPCGPU_ERR_CUDA; }
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, a, b);
+        const double fl = 2.0 * 8.0 * (double)iters * blocks * threads;
+        const double tf = fl / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    cudaFree(d);
+    *tflops = best;
+    return MPCGPU_OK;
+}

@@ -1,3 +1,4 @@
 """mpcgpu: B200-native batched closed-loop MPC evaluation behind the reference's evaluator API."""
 from .plant import Channels, c2d_fopdt, simulate, cond_min  # noqa: F401
 from .problems import LinearProblem, shell3x3, woodberry, shell7x5, synthetic_population, CASES  # noqa: F401
+from .api import Evaluator, MpcGpuError, closedloop_toolbox, gam_fun, vns_cost, measure_fp64_peak, row2col, col2row  # noqa: F401

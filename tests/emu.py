@@ -1,0 +1,40 @@
+"""TEST-ONLY loader of tests/host_emulation/libmpcemu.so (lane-serialised host build of the kernel source)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from mpcgpu._capi import make_problem_struct, ProblemStruct
+
+_HERE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "host_emulation")
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        subprocess.check_call(["make", "-C", _HERE, "-s", "libmpcemu.so"])
+        _lib = C.CDLL(os.path.join(_HERE, "libmpcemu.so"))
+    return _lib
+
+
+def eval_batch(prob, N, Nu, delta, lam, mode="gam", traj=False, r=None, v=None, yref=None, nit=None):
+    ps, keep = make_problem_struct(prob, r=r, v=v, yref=yref, nit=nit)
+    nit = ps.nit
+    N = np.ascontiguousarray(N, dtype=np.int32); Nu = np.ascontiguousarray(Nu, dtype=np.int32)
+    n = len(N)
+    dl = np.ascontiguousarray(delta, dtype=np.float64).reshape(n, prob.ny)
+    lm = np.ascontiguousarray(lam, dtype=np.float64).reshape(n, prob.nu)
+    m = {"raw": 0, "gam": 1, "vns": 2}[mode]
+    cost = np.zeros((n, prob.ny) if m == 1 else (n,))
+    status = np.zeros(n, dtype=np.int32)
+    counters = np.zeros(2, dtype=np.uint64)
+    tr = [np.zeros((n, prob.ny, nit)), np.zeros((n, prob.nu, nit)), np.zeros((n, prob.ny, nit)), np.zeros((n, prob.nu, nit))] if traj else [None] * 4
+    P = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None else None
+    err = C.create_string_buffer(256)
+    rc = lib().emu_eval_batch(C.byref(ps), n, P(N), P(Nu), P(dl), P(lm), m, P(cost), *[P(t) for t in tr], P(status),
+                              P(counters), err, 256)
+    if rc:
+        raise RuntimeError(err.value.decode())
+    return cost, status, counters, tr

@@ -1,0 +1,57 @@
+"""CPU-side check of the *kernel source*: csrc/mpc_core.cuh compiled lane-serialised for the host
+(tests/host_emulation) against the oracle.  This is a debugging aid for the algorithm, not a product path;
+the CUDA build of the same source is checked on the GPU box by tests/test_gpu_parity.py."""
+import numpy as np
+import pytest
+
+import emu
+from mpcgpu import shell3x3, woodberry, synthetic_population
+from oracle import oracle as orc
+from parity_util import check_cost, hessian_cond, TOL_TRAJ, vns_well_posed
+
+
+@pytest.mark.parametrize("case,n", [("shell3x3", 160), ("woodberry", 96)])
+def test_gam_cost_parity(case, n):
+    p = {"shell3x3": lambda: shell3x3(2), "woodberry": woodberry}[case]()
+    op = orc.OracleProblem(p)
+    N, Nu, dl, lm = synthetic_population(p, n, seed=2)
+    g0, st0, stats = orc.eval_batch(op, N, Nu, dl, lm, "gam")
+    g1, st1, cnt, _ = emu.eval_batch(p, N, Nu, dl, lm, "gam")
+    assert (st0 == 0).all() and (st1 == 0).all()
+    rel = check_cost(g1, g0, hessian_cond(op, p, N, Nu, dl, lm), case)
+    assert np.median(rel) < 1e-10
+    assert int(cnt[0]) == int(stats[2])  # same number of QPs left the unconstrained fast path
+
+
+@pytest.mark.parametrize("case", ["shell3x3", "woodberry"])
+def test_trajectory_parity(case):
+    p = {"shell3x3": lambda: shell3x3(2), "woodberry": woodberry}[case]()
+    op = orc.OracleProblem(p)
+    N, Nu, dl, lm = synthetic_population(p, 24, seed=3, wlo=1e-3, whi=3.0)
+    _, st, _, tr = emu.eval_batch(p, N, Nu, dl, lm, "raw", traj=True)
+    assert (st == 0).all()
+    for c in range(24):
+        y, u, ys, uo, rc, _ = orc.closedloop(op, N[c], Nu[c], dl[c], lm[c])
+        for a, b in zip(tr, (y, u, ys, uo)):
+            assert np.abs(a[c] - b).max() < TOL_TRAJ
+
+
+@pytest.mark.parametrize("case", ["shell3x3", "woodberry"])
+def test_vns_cost_parity(case):
+    p = {"shell3x3": lambda: shell3x3(2), "woodberry": woodberry}[case]()
+    op = orc.OracleProblem(p)
+    N, Nu, dl, lm = synthetic_population(p, 24, seed=4, wlo=1e-3, whi=3.0)
+    F0, st0, _ = orc.eval_batch(op, N, Nu, dl, lm, "vns")
+    F1, st1, _, _ = emu.eval_batch(p, N, Nu, dl, lm, "vns")
+    ok = vns_well_posed(p, lambda r: orc.OracleProblem(p, r=r), N, Nu, dl, lm)
+    assert ok.sum() >= 12
+    rel = np.abs(F1 - F0) / np.abs(F0)
+    assert rel[ok].max() < 1e-6, rel
+
+
+def test_invalid_horizons_are_flagged():
+    p = shell3x3(2)
+    N = np.array([5, 300, 10, 20], dtype=np.int32); Nu = np.array([5, 3, 0, 4], dtype=np.int32)
+    dl = np.ones((4, 3)); lm = np.ones((4, 3))
+    g, st, _, _ = emu.eval_batch(p, N, Nu, dl, lm, "gam")
+    assert list(st) == [4, 4, 4, 0]

@@ -1,0 +1,163 @@
+"""GPU parity tests proper: libmpcgpu.so (CUDA, sm_100a) through the C ABI versus the CPU oracle.
+Tolerances (DESIGN.md "Tolerance"): 1e-6 relative on cost, 1e-5 absolute on trajectories
+(BASELINE.json north_star), relaxed to 20*cond(H)*eps only where fp64 cannot resolve 1e-6."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import mpcgpu
+from mpcgpu import shell3x3, woodberry, synthetic_population
+from oracle import oracle as orc
+from parity_util import check_cost, hessian_cond, TOL_TRAJ, vns_well_posed
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def ev3():
+    e = mpcgpu.Evaluator(shell3x3(2), device=0)
+    yield e
+    e.close()
+
+
+@pytest.fixture(scope="module")
+def evwb():
+    e = mpcgpu.Evaluator(woodberry(), device=0)
+    yield e
+    e.close()
+
+
+def test_extension_loaded_and_fp64_peak():
+    tf = mpcgpu.measure_fp64_peak(0)
+    assert 5.0 < tf < 80.0, tf     # B200 fp64 FMA: ~37 TFLOP/s nominal
+
+
+@pytest.mark.parametrize("case,n", [("shell3x3", 512), ("woodberry", 256)])
+def test_gam_cost_parity(case, n, ev3, evwb):
+    ev = ev3 if case == "shell3x3" else evwb
+    p = ev.prob
+    op = orc.OracleProblem(p)
+    N, Nu, dl, lm = synthetic_population(p, n, seed=2)
+    g0, st0, stats = orc.eval_batch(op, N, Nu, dl, lm, "gam")
+    c0 = ev.counters()
+    out = ev.eval_batch(N, Nu, dl, lm, mode="gam")
+    c1 = ev.counters()
+    assert (out["status"] == 0).all()
+    rel = check_cost(out["cost"], g0, hessian_cond(op, p, N, Nu, dl, lm), case)
+    assert np.median(rel) < 1e-10
+    assert c1["qp_constrained"] - c0["qp_constrained"] == int(stats[2])
+    assert c1["kernel_launches"] > c0["kernel_launches"]
+
+
+@pytest.mark.parametrize("case", ["shell3x3", "woodberry"])
+def test_trajectory_parity(case, ev3, evwb):
+    ev = ev3 if case == "shell3x3" else evwb
+    p = ev.prob
+    op = orc.OracleProblem(p)
+    N, Nu, dl, lm = synthetic_population(p, 48, seed=3, wlo=1e-3, whi=3.0)
+    out = ev.eval_batch(N, Nu, dl, lm, mode="raw")
+    assert (out["status"] == 0).all()
+    for c in range(48):
+        y, u, ys, uo, rc, _ = orc.closedloop(op, N[c], Nu[c], dl[c], lm[c])
+        for k, b in zip(("y", "u", "ys", "uopt"), (y, u, ys, uo)):
+            assert np.abs(out[k][c] - b).max() < TOL_TRAJ, (c, k)
+
+
+@pytest.mark.parametrize("case", ["shell3x3", "woodberry"])
+def test_vns_cost_parity(case, ev3, evwb):
+    ev = ev3 if case == "shell3x3" else evwb
+    p = ev.prob
+    op = orc.OracleProblem(p)
+    N, Nu, dl, lm = synthetic_population(p, 64, seed=4, wlo=1e-3, whi=3.0)
+    F0, st0, _ = orc.eval_batch(op, N, Nu, dl, lm, "vns")
+    out = ev.eval_batch(N, Nu, dl, lm, mode="vns")
+    assert (out["status"] == 0).all()
+    ok = vns_well_posed(p, lambda r: orc.OracleProblem(p, r=r), N, Nu, dl, lm)
+    assert ok.sum() >= 32
+    rel = np.abs(out["cost"] - F0) / np.abs(F0)
+    assert rel[ok].max() < 1e-6, rel
+
+
+def test_golden_fixture(ev3):
+    """Committed oracle outputs (tests/golden/make_oracle_golden.py) for fixed candidates incl. the
+    reference's two tuned Shell3x3 results."""
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "oracle_golden_shell3x3.npz"))
+    out = ev3.eval_batch(gold["N"], gold["Nu"], gold["delta"], gold["lam"], mode="gam", traj=True)
+    assert (out["status"] == 0).all()
+    rel = np.abs(out["cost"] - gold["gam"]) / np.abs(gold["gam"])
+    assert rel.max() < 1e-6
+    assert np.abs(out["y"][:, :, ::10] - gold["y_sub"]).max() < TOL_TRAJ
+    assert np.abs(out["u"][:, :, ::10] - gold["u_sub"]).max() < TOL_TRAJ
+    vns = ev3.eval_batch(gold["N"], gold["Nu"], gold["delta"], gold["lam"], mode="vns")
+    ok = gold["vns_ok"].astype(bool)
+    relv = np.abs(vns["cost"] - gold["vns"]) / np.abs(gold["vns"])
+    assert relv[ok].max() < 1e-6
+
+
+def test_closedloop_toolbox_signature(ev3):
+    """Drop-in call as Shell3x3.m:231: r_ma.*sel in signals x time orientation, nit_open = N + 30."""
+    p = ev3.prob
+    N, Nu = 24, [6, 2, 2]
+    delta = [0.010659948215964849, 0.004019856475662751, 0.0007926546087416782]
+    lam = [9.247457388705409e-05, 0.0005523146971406108, 0.0015219790494510478]
+    nit_open = N + 30
+    r_ma = (np.ones((3, nit_open)) * p.L[:, None]) * np.array([[1.0], [0.0], [0.0]])
+    y, u, t, ys, uopt = mpcgpu.closedloop_toolbox(ev3, r_ma, np.zeros((nit_open, 0)), N, Nu, delta, lam, nit_open)
+    assert y.shape == (3, nit_open) and u.shape == (3, nit_open) and t.shape == (1, nit_open)
+    op = orc.OracleProblem(p, r=r_ma.T, v=np.zeros((nit_open, 0)), nit=nit_open)
+    y0, u0, ys0, uo0, rc, _ = orc.closedloop(op, N, max(Nu), delta, lam)
+    for a, b in ((y, y0), (u, u0), (ys, ys0), (uopt, uo0)):
+        assert np.abs(a - b).max() < TOL_TRAJ
+    # restore the problem's own signals for the other tests
+    ev3.set_signals(p.r, None, p.yref, p.nit)
+
+
+def test_full_size_properties(ev3):
+    """BASELINE.json's full population (4096) through size-independent properties."""
+    p = ev3.prob
+    N, Nu, dl, lm = synthetic_population(p, 4096, seed=0)
+    a = ev3.eval_batch(N, Nu, dl, lm, mode="gam")
+    assert (a["status"] == 0).all() and np.isfinite(a["cost"]).all() and (a["cost"] >= 0).all()
+    b = ev3.eval_batch(N, Nu, dl, lm, mode="gam")
+    assert np.array_equal(a["cost"], b["cost"]), "not deterministic run-to-run"
+    perm = np.random.default_rng(0).permutation(4096)
+    c = ev3.eval_batch(N[perm], Nu[perm], dl[perm], lm[perm], mode="gam")
+    assert np.array_equal(a["cost"][perm], c["cost"]), "result depends on the position in the population"
+    # spot-check 64 of them against the oracle
+    idx = np.random.default_rng(1).choice(4096, 64, replace=False)
+    op = orc.OracleProblem(p)
+    g0, _, _ = orc.eval_batch(op, N[idx], Nu[idx], dl[idx], lm[idx], "gam")
+    check_cost(a["cost"][idx], g0, hessian_cond(op, p, N[idx], Nu[idx], dl[idx], lm[idx]), "full-size spot check")
+    # limits hold on a trajectory subset
+    t = ev3.eval_batch(N[:256], Nu[:256], dl[:256], lm[:256], mode="raw")
+    u = t["u"]
+    assert (u >= p.umin[None, :, None] - 1e-9).all() and (u <= p.umax[None, :, None] + 1e-9).all()
+    du = np.diff(np.concatenate([np.zeros((256, 3, 1)), u], axis=2), axis=2)
+    assert (np.abs(du) <= p.dumax[None, :, None] + 1e-9).all()
+
+
+def test_edge_cases(ev3):
+    p = ev3.prob
+    # empty population
+    out = ev3.eval_batch(np.zeros(0, np.int32), np.zeros(0, np.int32), np.zeros((0, 3)), np.zeros((0, 3)), mode="gam")
+    assert out["cost"].shape == (0, 3)
+    # illegal horizons are flagged, legal neighbours unaffected
+    N = np.array([5, 300, 10, 20, 127], dtype=np.int32); Nu = np.array([5, 3, 0, 4, 15], dtype=np.int32)
+    out = ev3.eval_batch(N, Nu, np.ones((5, 3)), np.ones((5, 3)), mode="gam")
+    assert list(out["status"]) == [4, 4, 4, 0, 0]
+    assert np.isnan(out["cost"][:3]).all() and np.isfinite(out["cost"][3:]).all()
+    # huge lambda freezes the controller: cost == sum(Yref^2)
+    out = ev3.eval_batch([30], [4], [[1e-3] * 3], [[1e9] * 3], mode="gam")
+    np.testing.assert_allclose(out["cost"][0], (p.yref ** 2).sum(axis=1), rtol=1e-6)
+    # maximum sizes
+    out = ev3.eval_batch([127], [15], [[1.0] * 3], [[0.1] * 3], mode="vns")
+    assert out["status"][0] == 0 and np.isfinite(out["cost"][0])
+    # gam_fun / vns_cost wrappers
+    ev3.N, ev3.Nu = 24, 6
+    g, h = mpcgpu.gam_fun([1, 1, 1, -0.1, 0.1, 0.1], ev3)
+    assert g.shape == (3,) and h.size == 0
+    F = mpcgpu.vns_cost(ev3, [24, 6, 24], [6, 2, 30], [1, 1, 1], [.1, .1, .1])
+    assert np.isfinite(F[0]) and np.isinf(F[1]) and np.isinf(F[2])
