@@ -150,6 +150,8 @@ def main():
     ap.add_argument("--pop", type=int, default=4096, help="candidates per GPU")
     ap.add_argument("--mode", default="gam", choices=["gam", "vns"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--fixed", default="", help="p,m : pin every candidate's horizons (diagnostic populations)")
+    ap.add_argument("--weights", default="", help="lo,hi : log-uniform weight range (default 1e-4,10)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -170,7 +172,9 @@ def main():
     prob = mpcgpu.shell3x3(2)
     nit = prob.nit
     # weak scaling: every rank evaluates its own `pop` candidates of one global seeded population
-    Ng, Nug, dg, lg = mpcgpu.synthetic_population(prob, args.pop * world, seed=0)
+    fixed = tuple(int(x) for x in args.fixed.split(",")) if args.fixed else None
+    wlo, whi = (float(x) for x in args.weights.split(",")) if args.weights else (1e-4, 10.0)
+    Ng, Nug, dg, lg = mpcgpu.synthetic_population(prob, args.pop * world, seed=0, fixed=fixed, wlo=wlo, whi=whi)
     sl = slice(rank, None, world)   # round-robin shard (sizes are i.i.d., so this is work-balanced)
     N, Nu, delta, lam = Ng[sl], Nug[sl], dg[sl], lg[sl]
     n = len(N)
@@ -178,7 +182,9 @@ def main():
     ncost = n * prob.ny if args.mode == "gam" else n
     gathered = torch.empty(ncost * world, dtype=torch.float64, device="cuda")
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")  # 256 MiB > 126 MB L2
-    stream = torch.cuda.current_stream().cuda_stream
+    tstream = torch.cuda.Stream()          # a real (non-NULL) stream: the events below must see the kernels
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
 
     class _DevView:
         def __init__(self, ptr, count):

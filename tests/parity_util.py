@@ -6,11 +6,12 @@ from oracle import oracle as orc
 EPS = 2.220446049250313e-16
 TOL_COST = 1e-6      # BASELINE.json north_star: 1e-6 relative on cost
 TOL_TRAJ = 1e-5      # ... 1e-5 on trajectories
-COND_FACTOR = 20.0   # conditioning-limited bound: 20 * cond(H) * eps (measured worst case 1.4)
+SENS_FACTOR = 10.0
+PERT = (3e-14, -2e-14)   # relative input perturbation (delta, lambda) used to probe well-posedness
 
 
 def hessian_cond(op, prob, N, Nu, delta, lam):
-    """cond_2 of the candidate's QP Hessian, from the oracle's own H."""
+    """cond_2 of the candidate's QP Hessian, from the oracle's own H (diagnostics)."""
     hl = int(prob.plant.d.max()) + 2
     nw = prob.nu + prob.nd
     out = np.zeros(len(N))
@@ -21,21 +22,31 @@ def hessian_cond(op, prob, N, Nu, delta, lam):
     return out
 
 
-def cost_tolerance(cond):
-    """1e-6 wherever fp64 resolves it; beyond that the QP data itself (H to 1 ulp) moves the answer by
-    ~cond(H)*eps, for the oracle as much as for the GPU (tests/test_oracle.py::test_oracle_fp_noise)."""
-    return np.maximum(TOL_COST, COND_FACTOR * cond * EPS)
+def oracle_sensitivity(op, N, Nu, delta, lam, mode, cost_ref):
+    """How far the ORACLE's own cost moves when delta, lambda are perturbed by ~100 ulp.  Two effects make
+    this large for a few candidates, for any fp64 implementation (DESIGN.md "Tolerance"):
+      * cond(H) up to 4e12 in the survey's weight range: H is only known to 1 ulp, the optimum moves by cond*eps;
+      * closed loops that are unstable/limit-cycling against the MV limits (e.g. N=7 is shorter than the
+        7-sample dead time of output 1): differences grow exponentially over the 500 samples."""
+    pert, _, _ = orc.eval_batch(op, N, Nu, np.asarray(delta) * (1 + PERT[0]), np.asarray(lam) * (1 + PERT[1]), mode)
+    rel = np.abs(pert - cost_ref) / np.maximum(np.abs(cost_ref), 1e-300)
+    return rel.max(axis=1) if rel.ndim == 2 else rel
 
 
-def check_cost(cost, cost_ref, cond, what=""):
+def check_cost(cost, cost_ref, sens, what="", min_strict=0.75):
+    """|cost - oracle| / |oracle| <= max(1e-6, 10 * oracle's own sensitivity).  At least `min_strict` of the
+    population must be held to the strict 1e-6."""
     cost = np.asarray(cost); cost_ref = np.asarray(cost_ref)
     rel = np.abs(cost - cost_ref) / np.maximum(np.abs(cost_ref), 1e-300)
     if rel.ndim == 2:
         rel = rel.max(axis=1)
-    tol = cost_tolerance(cond)
-    bad = np.where(rel > tol)[0]
-    assert len(bad) == 0, f"{what}: {len(bad)} candidates out of tolerance, worst rel {rel.max():.3e} (cond {cond[rel.argmax()]:.2e})"
-    return rel
+    tol = np.maximum(TOL_COST, SENS_FACTOR * sens)
+    bad = np.where(~(rel <= tol))[0]
+    assert len(bad) == 0, (f"{what}: {len(bad)} candidates out of tolerance, worst rel {rel[bad].max():.3e} "
+                           f"(tol {tol[bad][rel[bad].argmax()]:.2e}, candidate {bad[rel[bad].argmax()]})")
+    strict = float((tol <= TOL_COST).mean())
+    assert strict >= min_strict, f"{what}: only {strict:.2%} of the candidates are well-posed enough for the 1e-6 bar"
+    return rel, strict
 
 
 def vns_well_posed(prob, op_factory, N, Nu, delta, lam, thresh=1e-7):
