@@ -152,6 +152,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--fixed", default="", help="p,m : pin every candidate's horizons (diagnostic populations)")
     ap.add_argument("--weights", default="", help="lo,hi : log-uniform weight range (default 1e-4,10)")
+    ap.add_argument("--lam", default="", help="lo,hi : override the lambda range only (diagnostics)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -175,6 +176,9 @@ def main():
     fixed = tuple(int(x) for x in args.fixed.split(",")) if args.fixed else None
     wlo, whi = (float(x) for x in args.weights.split(",")) if args.weights else (1e-4, 10.0)
     Ng, Nug, dg, lg = mpcgpu.synthetic_population(prob, args.pop * world, seed=0, fixed=fixed, wlo=wlo, whi=whi)
+    if args.lam:
+        llo, lhi = (float(x) for x in args.lam.split(","))
+        lg = np.exp(np.random.default_rng(5).uniform(np.log(llo), np.log(lhi), size=lg.shape))
     sl = slice(rank, None, world)   # round-robin shard (sizes are i.i.d., so this is work-balanced)
     N, Nu, delta, lam = Ng[sl], Nug[sl], dg[sl], lg[sl]
     n = len(N)

@@ -206,6 +206,7 @@ struct MpcSimSmem {
     double *hbuf;   // hmax    scratch for the history shift
     int *act;       // nz      active constraint ids: type*nz + e
     int *amask;     // nz      4 bits per variable
+    int *dflag;     // nz      drop flags (scratch)
 };
 
 static MPC_HD int mpc_hmax(const MpcLayout &L) {
@@ -218,7 +219,7 @@ static MPC_HD size_t mpc_sim_smem_doubles(const MpcLayout &L, int m) {
     const int nz = L.nu * m;
     size_t n = (size_t)L.nst * nz + L.ns + L.nst + 8 * (size_t)nz + (size_t)nz * (nz + 1) / 2 + L.ny * L.nw + L.nu * m + L.nu +
                3 * L.ny + mpc_hmax(L);
-    n += (2 * (size_t)nz + 1) / 2 + 1;  // two int arrays
+    n += (3 * (size_t)nz + 1) / 2 + 1;  // three int arrays
     return n;
 }
 
@@ -245,9 +246,15 @@ MPC_FN void mpc_sim_carve(const MpcLayout &L, int m, double *base, MpcSimSmem &s
     sm.hbuf = p; p += mpc_hmax(L);
     sm.act = (int *)p;
     sm.amask = sm.act + nz;
+    sm.dflag = sm.amask + nz;
 }
 
-// slack of constraint `type` on variable e given level lvl (u_prev + cumulative moves)
+// ---------------------------------------------------------------------------------------------
+// Constraint ids: cid = type | (e << 2), e = c*NU + j the move index.
+//   type 0: dz_e >= dumin_j      1: dz_e <= dumax_j        (MV rate, n = +-e_e)
+//   type 2: u_j(k+c) >= umin_j   3: u_j(k+c) <= umax_j     (MV level, n = +-sum_{c'<=c} e_(c',j))
+// All are hard (MV ECR = 0, oracle T4).
+// ---------------------------------------------------------------------------------------------
 MPC_FN double mpc_slack(const MpcLayout &L, int type, int j, double ze, double lvl) {
     switch (type) {
         case 0: return ze - L.dumin[j];
@@ -257,49 +264,92 @@ MPC_FN double mpc_slack(const MpcLayout &L, int type, int j, double ze, double l
     }
 }
 
-// n_a[e] for constraint id `cid` (0 / +-1)
-MPC_FN double mpc_normal_entry(int cid, int nz, int nu, int e) {
-    const int type = cid / nz, ea = cid - type * nz;
+template <int NU>
+MPC_FN double mpc_level(const MpcSimSmem &sm, int c, int j) {
+    double lvl = sm.uprev[j];
+    for (int c2 = 0; c2 <= c; ++c2) lvl += sm.z[c2 * NU + j];
+    return lvl;
+}
+
+// n_a[e] for constraint cid (0 / +-1)
+template <int NU>
+MPC_FN double mpc_normal_entry(int cid, int e) {
+    const int type = cid & 3, ea = cid >> 2;
     if (type < 2) return (e == ea) ? (type == 0 ? 1.0 : -1.0) : 0.0;
-    const int ca = ea / nu, ja = ea - ca * nu;
-    const int c = e / nu, j = e - c * nu;
+    const int ca = ea / NU, ja = ea - ca * NU;
+    const int c = e / NU, j = e - c * NU;
     return (j == ja && c <= ca) ? (type == 2 ? 1.0 : -1.0) : 0.0;
 }
 
 // n_a' x for a dense vector x in shared memory
-MPC_FN double mpc_normal_dot(int cid, int nz, int nu, const double *x) {
-    const int type = cid / nz, ea = cid - type * nz;
+template <int NU>
+MPC_FN double mpc_normal_dot(int cid, const double *x) {
+    const int type = cid & 3, ea = cid >> 2;
     if (type < 2) return type == 0 ? x[ea] : -x[ea];
-    const int ca = ea / nu, ja = ea - ca * nu;
+    const int ca = ea / NU, ja = ea - ca * NU;
     double acc = 0.0;
-    for (int c = 0; c <= ca; ++c) acc += x[c * nu + ja];
+    for (int c = 0; c <= ca; ++c) acc += x[c * NU + ja];
     return type == 2 ? acc : -acc;
 }
 
-// w = W n_p  (W symmetric, global memory, read coalesced as rows)
-MPC_FN void mpc_w_times_normal(int cid, int nz, int nu, const double *W, double *w) {
-    const int type = cid / nz, ea = cid - type * nz;
+// w = W n  (W symmetric, global memory, read coalesced as rows)
+template <int NU>
+MPC_FN void mpc_w_times_normal(int cid, int nz, const double *W, double *w) {
+    const int type = cid & 3, ea = cid >> 2;
     if (type < 2) {
         const double sg = type == 0 ? 1.0 : -1.0;
         LANE_FOR(e, nz) w[e] = sg * W[(size_t)ea * nz + e];
     } else {
-        const int ca = ea / nu, ja = ea - ca * nu;
+        const int ca = ea / NU, ja = ea - ca * NU;
         const double sg = type == 2 ? 1.0 : -1.0;
         LANE_FOR(e, nz) {
             double acc = 0.0;
-            for (int c = 0; c <= ca; ++c) acc += W[(size_t)(c * nu + ja) * nz + e];
+#pragma unroll 4
+            for (int c = 0; c <= ca; ++c) acc += W[(size_t)(c * NU + ja) * nz + e];
             w[e] = sg * acc;
         }
     }
 }
 
+// z += scale * W v   (v in shared memory)
+MPC_FN void mpc_add_W_times(int nz, const double *W, const double *v, double scale, double *z) {
+    LANE_FOR(e, nz) {
+        double a0 = 0.0, a1 = 0.0;
+        int e2 = 0;
+#pragma unroll 4
+        for (; e2 + 1 < nz; e2 += 2) {
+            a0 += W[(size_t)e2 * nz + e] * v[e2];
+            a1 += W[(size_t)(e2 + 1) * nz + e] * v[e2 + 1];
+        }
+        if (e2 < nz) a0 += W[(size_t)e2 * nz + e] * v[e2];
+        z[e] += scale * (a0 + a1);
+    }
+}
+
 MPC_FN double mpc_Li(const double *Li, int a, int b) { return Li[(a * (a + 1)) / 2 + b]; }  // b <= a
 
-// Append constraint cid (whose w = W n is in sm.w) to the factor at position q.
-// Computes g, l, rho; returns rho (Schur pivot) and gamma through *gamma_out.  Does not commit.
-MPC_FN double mpc_schur_column(int cid, int q, int nz, int nu, MpcSimSmem &sm, double *gamma_out) {
-    const double gamma = mpc_normal_dot(cid, nz, nu, sm.w);
-    LANE_FOR(a, q) sm.g[a] = mpc_normal_dot(sm.act[a], nz, nu, sm.w);
+// out = S^-1 rhs with S^-1 = Li' Li  (rhs, out: length q in shared memory; tmp = sm.l)
+MPC_FN void mpc_schur_solve(int q, const MpcSimSmem &sm, const double *rhs, double *out) {
+    LANE_FOR(a, q) {
+        double acc = 0.0;
+        for (int b = 0; b <= a; ++b) acc += mpc_Li(sm.Li, a, b) * rhs[b];
+        sm.l[a] = acc;
+    }
+    WSYNC();
+    LANE_FOR(a, q) {
+        double acc = 0.0;
+        for (int b = a; b < q; ++b) acc += mpc_Li(sm.Li, b, a) * sm.l[b];
+        out[a] = acc;
+    }
+    WSYNC();
+}
+
+// Schur column of constraint cid against the first q active constraints; wv = W n_cid.
+// Leaves g = N'wv, l = Li g, rr = Li' l in shared memory; returns rho = gamma - |l|^2.
+template <int NU>
+MPC_FN double mpc_schur_column(int cid, int q, const double *wv, MpcSimSmem &sm, double *gamma_out) {
+    const double gamma = mpc_normal_dot<NU>(cid, wv);
+    LANE_FOR(a, q) sm.g[a] = mpc_normal_dot<NU>(sm.act[a], wv);
     WSYNC();
     double part = 0.0;
     LANE_FOR(a, q) {
@@ -320,8 +370,8 @@ MPC_FN double mpc_schur_column(int cid, int q, int nz, int nu, MpcSimSmem &sm, d
     return gamma - l2;
 }
 
-// Commit: new row of Linv_c = [-r'/sqrt(rho), 1/sqrt(rho)]
-MPC_FN void mpc_schur_commit(int cid, int q, int nz, double rho, double mu_new, MpcSimSmem &sm) {
+// Commit constraint cid at position q: new row of Linv_c = [-r'/sqrt(rho), 1/sqrt(rho)]
+MPC_FN void mpc_schur_commit(int cid, int q, double rho, double mu_new, MpcSimSmem &sm) {
     const double isr = 1.0 / sqrt(rho);
     double *row = sm.Li + (q * (q + 1)) / 2;
     LANE_FOR(a, q) row[a] = -sm.rr[a] * isr;
@@ -329,34 +379,103 @@ MPC_FN void mpc_schur_commit(int cid, int q, int nz, double rho, double mu_new, 
         row[q] = isr;
         sm.act[q] = cid;
         sm.mu[q] = mu_new;
-        const int type = cid / nz, e = cid - type * nz;
-        sm.amask[e] |= (1 << type);
+        sm.amask[cid >> 2] |= (1 << (cid & 3));
     }
     WSYNC();
 }
 
-// Dual active-set QP (Goldfarb-Idnani logic on the Schur complement S = N' W N).
-// In: sm.z = unconstrained optimum, sm.uprev.  Out: sm.z = optimum.  Returns status (0 ok).
-MPC_FN int mpc_qp_active_set(const MpcLayout &L, int m, const double *W, MpcSimSmem &sm, int *iters_out) {
-    const int nu = L.nu, nz = nu * m;
-    int q = 0, it = 0;
+// Remove every active constraint whose drop flag (sm.dflag[a] != 0) is set, keeping the order of the
+// rest, and rebuild the factor rows from the first removed position on.  Returns the new q.
+template <int NU>
+MPC_FN int mpc_drop_flagged(int q, int nz, const double *W, MpcSimSmem &sm) {
+    int first = -1, qn = 0;
+    for (int a = 0; a < q; ++a) {  // uniform, sequential: q <= nz is small
+        const int fl = sm.dflag[a];
+        const int cid = sm.act[a];
+        const double mua = sm.mu[a];
+        WSYNC();
+        if (fl) {
+            if (first < 0) first = a;
+            if (IS_LANE0) sm.amask[cid >> 2] &= ~(1 << (cid & 3));
+        } else {
+            if (IS_LANE0) { sm.act[qn] = cid; sm.mu[qn] = mua; }
+            qn += 1;
+        }
+        WSYNC();
+    }
+    if (first < 0) return q;
+    for (int a = first; a < qn; ++a) {
+        const int cid = sm.act[a];
+        const double mua = sm.mu[a];
+        mpc_w_times_normal<NU>(cid, nz, W, sm.dir);
+        WSYNC();
+        double gam2;
+        const double rho2 = mpc_schur_column<NU>(cid, a, sm.dir, sm, &gam2);
+        mpc_schur_commit(cid, a, rho2 > 0.0 ? rho2 : MPC_DEP_TOL * gam2, mua, sm);
+    }
+    return qn;
+}
+
+// Dual active-set QP (Goldfarb-Idnani step logic on the Schur complement S = N'WN of the active
+// normals in the metric W = H^-1), WARM-STARTED: the active set and its factor survive from the
+// previous sample (the Toolbox solver does the same: Optimizer.ActiveSetOptions.UseWarmStart = 1 in the
+// reference's saved objects).  A warm start only changes the path, never the optimum (strictly convex).
+//   in : sm.z = unconstrained optimum z_unc, sm.uprev, q_io = carried active-set size
+//   out: sm.z = constrained optimum, q_io = final active-set size.  Returns status.
+template <int NU>
+MPC_FN int mpc_qp_active_set(const MpcLayout &L, int m, const double *W, MpcSimSmem &sm, int &q_io, int *iters_out) {
+    const int nz = NU * m;
+    int q = q_io, it = 0;
     const int itmax = 20 * (nz + 10);
-    LANE_FOR(e, nz) sm.amask[e] = 0;
-    WSYNC();
+    // ---- warm start: solve the equality-constrained problem on the carried set, shed negative multipliers
+    while (q > 0) {
+        LANE_FOR(a, q) {
+            const int cid = sm.act[a];
+            const int e = cid >> 2, c = e / NU, j = e - c * NU;
+            sm.g[a] = -mpc_slack(L, cid & 3, j, sm.z[e], mpc_level<NU>(sm, c, j));
+        }
+        WSYNC();
+        mpc_schur_solve(q, sm, sm.g, sm.mu);
+        double mumax = 0.0;
+        LANE_FOR(a, q) mumax = fmax(mumax, fabs(sm.mu[a]));
+        mumax = wmax(mumax);
+        int ndrop = 0;
+        LANE_FOR(a, q) {
+            const int fl = sm.mu[a] < -1e-12 * mumax;
+            sm.dflag[a] = fl;
+            ndrop |= fl;
+        }
+        ndrop = wany(ndrop);
+        WSYNC();
+        if (!ndrop) break;
+        it += 1;
+        q = mpc_drop_flagged<NU>(q, nz, W, sm);
+    }
+    if (q > 0) {  // z = z_unc + W N mu
+        LANE_FOR(a, q) if (sm.mu[a] < 0.0) sm.mu[a] = 0.0;
+        WSYNC();
+        LANE_FOR(e, nz) {
+            double acc = 0.0;
+            for (int a = 0; a < q; ++a) acc += sm.mu[a] * mpc_normal_entry<NU>(sm.act[a], e);
+            sm.vv[e] = acc;
+        }
+        WSYNC();
+        mpc_add_W_times(nz, W, sm.vv, 1.0, sm.z);
+        WSYNC();
+    }
+    // ---- Goldfarb-Idnani iterations from the S-pair (z, A) ----
     for (;;) {
-        // ---- most violated inactive constraint ----
         double bv = -MPC_VIOL_TOL;
         int bi = -1;
         LANE_FOR(e, nz) {
-            const int c = e / nu, j = e - c * nu;
-            double lvl = sm.uprev[j];
-            for (int c2 = 0; c2 <= c; ++c2) lvl += sm.z[c2 * nu + j];
+            const int c = e / NU, j = e - c * NU;
+            const double lvl = mpc_level<NU>(sm, c, j);
             const double ze = sm.z[e];
             const int am = sm.amask[e];
             for (int type = 0; type < 4; ++type) {
                 if (am & (1 << type)) continue;
                 const double sl = mpc_slack(L, type, j, ze, lvl);
-                const int id = type * nz + e;
+                const int id = type | (e << 2);
                 if (sl < bv || (sl == bv && bi >= 0 && id < bi)) { bv = sl; bi = id; }
             }
         }
@@ -364,14 +483,13 @@ MPC_FN int mpc_qp_active_set(const MpcLayout &L, int m, const double *W, MpcSimS
         if (bi < 0) break;
         const int p = bi;
         double sp = bv, mu_p = 0.0;
-        mpc_w_times_normal(p, nz, nu, W, sm.w);
+        mpc_w_times_normal<NU>(p, nz, W, sm.w);
         WSYNC();
         for (;;) {
-            if (++it > itmax) { *iters_out = it; return 2; }
+            if (++it > itmax) { *iters_out = it; q_io = q; return 2; }
             double gamma;
-            const double rho = mpc_schur_column(p, q, nz, nu, sm, &gamma);
+            const double rho = mpc_schur_column<NU>(p, q, sm.w, sm, &gamma);
             const int dependent = !(rho > MPC_DEP_TOL * gamma);
-            // dual step length
             double t1 = MPC_INF;
             int l1 = -1;
             LANE_FOR(a, q) {
@@ -384,63 +502,30 @@ MPC_FN int mpc_qp_active_set(const MpcLayout &L, int m, const double *W, MpcSimS
             wargmin(t1, l1);
             const double t2 = dependent ? MPC_INF : -sp / rho;
             const double t = t1 < t2 ? t1 : t2;
-            if (!(t < MPC_INF)) { *iters_out = it; return 1; }
+            if (!(t < MPC_INF)) { *iters_out = it; q_io = q; return 1; }
             const int full = !(dependent || t1 < t2);
-            if (!dependent) {
-                // dir = W (n_p - N r)
+            if (!dependent) {  // primal step along dir = W (n_p - N r)
                 LANE_FOR(e, nz) {
-                    double acc = mpc_normal_entry(p, nz, nu, e);
-                    for (int a = 0; a < q; ++a) acc -= sm.rr[a] * mpc_normal_entry(sm.act[a], nz, nu, e);
+                    double acc = mpc_normal_entry<NU>(p, e);
+                    for (int a = 0; a < q; ++a) acc -= sm.rr[a] * mpc_normal_entry<NU>(sm.act[a], e);
                     sm.vv[e] = acc;
                 }
                 WSYNC();
-                LANE_FOR(e, nz) {
-                    double acc = 0.0;
-                    for (int e2 = 0; e2 < nz; ++e2) acc += W[(size_t)e2 * nz + e] * sm.vv[e2];
-                    sm.z[e] += t * acc;
-                }
+                mpc_add_W_times(nz, W, sm.vv, t, sm.z);
                 sp += t * rho;
             }
-            LANE_FOR(a, q) sm.mu[a] -= t * sm.rr[a];
+            LANE_FOR(a, q) {
+                sm.mu[a] -= t * sm.rr[a];
+                sm.dflag[a] = (a == l1) && !full;
+            }
             mu_p += t;
             WSYNC();
             if (full) {
-                mpc_schur_commit(p, q, nz, rho, mu_p, sm);
+                mpc_schur_commit(p, q, rho, mu_p, sm);
                 q += 1;
                 break;
             }
-            // ---- drop constraint at position l1, rebuild the factor rows behind it ----
-            {
-                if (IS_LANE0) {
-                    const int cid = sm.act[l1];
-                    const int type = cid / nz, e = cid - type * nz;
-                    sm.amask[e] &= ~(1 << type);
-                }
-                WSYNC();
-                const int qold = q;
-                // compact lists (order kept), then re-append positions l1..q-2
-                for (int a = l1; a < qold - 1; ++a) {
-                    const int cid = sm.act[a + 1];
-                    const double mua = sm.mu[a + 1];
-                    WSYNC();
-                    if (IS_LANE0) { sm.act[a] = cid; sm.mu[a] = mua; }
-                    WSYNC();
-                }
-                q = l1;
-                for (int a = l1; a < qold - 1; ++a) {
-                    const int cid = sm.act[a];
-                    const double mua = sm.mu[a];
-                    mpc_w_times_normal(cid, nz, nu, W, sm.dir);  // dir used as scratch for W n_a
-                    WSYNC();
-                    double *wkeep = sm.w;
-                    sm.w = sm.dir;
-                    double gam2;
-                    const double rho2 = mpc_schur_column(cid, q, nz, nu, sm, &gam2);
-                    sm.w = wkeep;
-                    mpc_schur_commit(cid, q, nz, rho2 > 0.0 ? rho2 : MPC_DEP_TOL * gam2, mua, sm);
-                    q += 1;
-                }
-            }
+            q = mpc_drop_flagged<NU>(q, nz, W, sm);
         }
     }
     // ---- one Newton correction on the active constraints if they drifted ----
@@ -448,71 +533,57 @@ MPC_FN int mpc_qp_active_set(const MpcLayout &L, int m, const double *W, MpcSimS
         double worst = 0.0;
         LANE_FOR(a, q) {
             const int cid = sm.act[a];
-            const int type = cid / nz, e = cid - type * nz;
-            const int c = e / nu, j = e - c * nu;
-            double lvl = sm.uprev[j];
-            for (int c2 = 0; c2 <= c; ++c2) lvl += sm.z[c2 * nu + j];
-            const double sl = mpc_slack(L, type, j, sm.z[e], lvl);
-            sm.g[a] = sl;
+            const int e = cid >> 2, c = e / NU, j = e - c * NU;
+            const double sl = mpc_slack(L, cid & 3, j, sm.z[e], mpc_level<NU>(sm, c, j));
+            sm.g[a] = -sl;
             worst = fmax(worst, fabs(sl));
         }
         worst = wmax(worst);
         WSYNC();
         if (worst > 1e-13) {
-            LANE_FOR(a, q) {
-                double acc = 0.0;
-                for (int b = 0; b <= a; ++b) acc += mpc_Li(sm.Li, a, b) * sm.g[b];
-                sm.l[a] = acc;
-            }
-            WSYNC();
-            LANE_FOR(a, q) {
-                double acc = 0.0;
-                for (int b = a; b < q; ++b) acc += mpc_Li(sm.Li, b, a) * sm.l[b];
-                sm.rr[a] = -acc;  // delta mu
-            }
-            WSYNC();
+            mpc_schur_solve(q, sm, sm.g, sm.rr);  // delta mu
             LANE_FOR(e, nz) {
                 double acc = 0.0;
-                for (int a = 0; a < q; ++a) acc += sm.rr[a] * mpc_normal_entry(sm.act[a], nz, nu, e);
+                for (int a = 0; a < q; ++a) acc += sm.rr[a] * mpc_normal_entry<NU>(sm.act[a], e);
                 sm.vv[e] = acc;
             }
             WSYNC();
-            LANE_FOR(e, nz) {
-                double acc = 0.0;
-                for (int e2 = 0; e2 < nz; ++e2) acc += W[(size_t)e2 * nz + e] * sm.vv[e2];
-                sm.z[e] += acc;
-            }
+            mpc_add_W_times(nz, W, sm.vv, 1.0, sm.z);
             WSYNC();
         }
     }
     *iters_out = it;
+    q_io = q;
     return 0;
 }
 
-// z = M s, then the box / rate check; runs the active-set QP when violated.
-MPC_FN int mpc_controller_move(const MpcLayout &L, int m, const double *W, MpcSimSmem &sm, int *constrained,
+// z = M st, then the box / rate check; runs the active-set QP when the check fails or when an active
+// set is carried over from the previous sample.
+template <int NU>
+MPC_FN int mpc_controller_move(const MpcLayout &L, int m, const double *W, MpcSimSmem &sm, int &q_io, int *constrained,
                                int *iters) {
-    const int nu = L.nu, ny = L.ny, nw = L.nw, nz = nu * m, ns = L.nst;
+    const int ny = L.ny, nw = L.nw, nz = NU * m, ns = L.nst;
     // deviation coordinates (mpc_layout.h): everything relative to the steady state of the held inputs
     LANE_FOR(ch, ny * nw) {
         const int j = ch % nw;
-        const double hv = j < nu ? sm.s[L.hoff[j]] : sm.s[L.off_v + (j - nu)];
+        const double hv = j < NU ? sm.s[L.hoff[j]] : sm.s[L.off_v + (j - NU)];
         sm.st[ch] = sm.s[ch] - L.gain[ch] * hv;
     }
     for (int j = 0; j < nw; ++j) {
         const int q0 = L.hq0[j], nq = L.hlen[j] - q0;
-        const double hv = j < nu ? sm.s[L.hoff[j]] : sm.s[L.off_v + (j - nu)];
+        const double hv = j < NU ? sm.s[L.hoff[j]] : sm.s[L.off_v + (j - NU)];
         LANE_FOR(qq, nq) sm.st[L.stoff_h[j] + qq] = sm.s[L.hoff[j] + q0 + qq] - hv;
     }
     LANE_FOR(i, ny) {
         double acc = sm.s[L.off_r + i];
-        for (int j = 0; j < nw; ++j) acc -= L.gain[i * nw + j] * (j < nu ? sm.s[L.hoff[j]] : sm.s[L.off_v + (j - nu)]);
+        for (int j = 0; j < nw; ++j) acc -= L.gain[i * nw + j] * (j < NU ? sm.s[L.hoff[j]] : sm.s[L.off_v + (j - NU)]);
         sm.st[L.stoff_e + i] = acc;
     }
     WSYNC();
     LANE_FOR(e, nz) {
         double a0 = 0.0, a1 = 0.0;
         int sg = 0;
+#pragma unroll 4
         for (; sg + 1 < ns; sg += 2) {
             a0 += sm.M[(size_t)sg * nz + e] * sm.st[sg];
             a1 += sm.M[(size_t)(sg + 1) * nz + e] * sm.st[sg + 1];
@@ -521,20 +592,23 @@ MPC_FN int mpc_controller_move(const MpcLayout &L, int m, const double *W, MpcSi
         sm.z[e] = a0 + a1;
     }
     WSYNC();
-    int bad = 0;
-    LANE_FOR(e, nz) {
-        const int c = e / nu, j = e - c * nu;
-        double lvl = sm.uprev[j];
-        for (int c2 = 0; c2 <= c; ++c2) lvl += sm.z[c2 * nu + j];
-        const double ze = sm.z[e];
-        bad |= (ze - L.dumin[j] < -MPC_VIOL_TOL) | (L.dumax[j] - ze < -MPC_VIOL_TOL) |
-               (lvl - L.umin[j] < -MPC_VIOL_TOL) | (L.umax[j] - lvl < -MPC_VIOL_TOL);
-    }
-    bad = wany(bad);
-    *constrained = bad;
     *iters = 0;
-    if (!bad) return 0;
-    return mpc_qp_active_set(L, m, W, sm, iters);
+    if (q_io == 0) {
+        int bad = 0;
+        LANE_FOR(e, nz) {
+            const int c = e / NU, j = e - c * NU;
+            const double lvl = mpc_level<NU>(sm, c, j);
+            const double ze = sm.z[e];
+            bad |= (ze - L.dumin[j] < -MPC_VIOL_TOL) | (L.dumax[j] - ze < -MPC_VIOL_TOL) |
+                   (lvl - L.umin[j] < -MPC_VIOL_TOL) | (L.umax[j] - lvl < -MPC_VIOL_TOL);
+        }
+        bad = wany(bad);
+        *constrained = bad;
+        if (!bad) return 0;
+    } else {
+        *constrained = 1;
+    }
+    return mpc_qp_active_set<NU>(L, m, W, sm, q_io, iters);
 }
 
 // One plant sample for channel ch=(i,j): x(k+1) = a x(k) + b0 w(k+1-d) + b1 w(k-d)
@@ -554,9 +628,10 @@ struct MpcRunOut {
 
 // sel: -2 user set-point (GAM / RAW);  -1 VNS step on every output;  i>=0 VNS step on output i only.
 // mode: 0 RAW, 1 GAM, 2 VNS.  Returns status.
+template <int NU>
 MPC_FN int mpc_sim_run(const MpcLayout &L, const MpcTables &T, int p, int m, const double *Mg, const double *W,
                        int mode, int sel, double *smem_base, const MpcRunOut &out) {
-    const int ny = L.ny, nu = L.nu, nd = L.nd, nw = L.nw, nz = nu * m, ns = L.ns, nit = L.nit;
+    const int ny = L.ny, nu = NU, nd = L.nd, nw = L.nw, nz = NU * m, ns = L.ns, nit = L.nit;
     MpcSimSmem sm;
     mpc_sim_carve(L, m, smem_base, sm);
     double *cost_local = sm.cost;
@@ -565,8 +640,10 @@ MPC_FN int mpc_sim_run(const MpcLayout &L, const MpcTables &T, int p, int m, con
     LANE_FOR(i, ny * nw) sm.xol[i] = 0.0;
     LANE_FOR(j, nu) sm.uprev[j] = 0.0;
     LANE_FOR(i, nu * m) sm.uopt[i] = 0.0;
+    LANE_FOR(e, nz) sm.amask[e] = 0;
     WSYNC();
     int status = 0;
+    int qact = 0;  // carried active-set size (warm start)
     unsigned long long n_con = 0, n_it = 0;
     const bool want_ol = (mode != 1) || out.ys || out.uopt;
     double jnu = 0.0;  // uniform
@@ -581,7 +658,7 @@ MPC_FN int mpc_sim_run(const MpcLayout &L, const MpcTables &T, int p, int m, con
         LANE_FOR(j, nd) sm.s[L.off_v + j] = T.v[(size_t)(nit - 1) * nd + j];
         WSYNC();
         int con, its;
-        const int rc = mpc_controller_move(L, m, W, sm, &con, &its);
+        const int rc = mpc_controller_move<NU>(L, m, W, sm, qact, &con, &its);
         if (rc) status = rc;
         n_con += con ? 1 : 0; n_it += its;
         LANE_FOR(j, nu) {
@@ -606,6 +683,8 @@ MPC_FN int mpc_sim_run(const MpcLayout &L, const MpcTables &T, int p, int m, con
             jnu = wsum(part);
         }
         LANE_FOR(i, ns) sm.s[i] = 0.0;
+        LANE_FOR(e, nz) sm.amask[e] = 0;   // the closed loop starts from an empty active set
+        qact = 0;
         WSYNC();
     }
     LANE_FOR(i, ny) cost_local[i] = 0.0;
@@ -635,7 +714,7 @@ MPC_FN int mpc_sim_run(const MpcLayout &L, const MpcTables &T, int p, int m, con
         LANE_FOR(j, nd) sm.s[L.off_v + j] = T.v[(size_t)k * nd + j];
         WSYNC();
         int con, its;
-        const int rc = mpc_controller_move(L, m, W, sm, &con, &its);
+        const int rc = mpc_controller_move<NU>(L, m, W, sm, qact, &con, &its);
         if (rc) status = rc;
         n_con += con ? 1 : 0; n_it += its;
         // apply the first move

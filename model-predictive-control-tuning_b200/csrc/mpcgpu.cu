@@ -67,6 +67,7 @@ __global__ void __launch_bounds__(BUILD_THREADS) k_build(const MpcLayout L, cons
 }
 
 // One warp per (candidate, run).  mode: 0 RAW, 1 GAM, 2 VNS.
+template <int NU>
 __global__ void __launch_bounds__(32) k_sim(const MpcLayout L, const MpcTables T, const int *order, int count, int runs,
                                             int mode, int square, DevCand C, DevOut O) {
     extern __shared__ double smem_s[];
@@ -92,7 +93,7 @@ __global__ void __launch_bounds__(32) k_sim(const MpcLayout L, const MpcTables T
     out.uopt = O.uopt ? O.uopt + (size_t)c * nu * nit : nullptr;
     out.counters = O.counters;
     const int sel = mode == 2 ? (square ? run : -1) : -2;
-    const int st = mpc_sim_run(L, T, p, m, C.M + C.offM[c], C.W + C.offW[c], mode, sel, smem_s, out);
+    const int st = mpc_sim_run<NU>(L, T, p, m, C.M + C.offM[c], C.W + C.offW[c], mode, sel, smem_s, out);
     if (st != 0 && (threadIdx.x & 31) == 0) atomicMax(O.status + c, st);
 }
 
@@ -258,7 +259,10 @@ extern "C" int mpcgpu_create(const mpcgpu_problem *problem, int device, mpcgpu_h
     if ((ce = h->dCounters.ensure(4)) != cudaSuccess) return fail("alloc counters", ce);
     // allow large dynamic shared memory on both kernels
     cudaFuncSetAttribute(k_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin);
-    cudaFuncSetAttribute(k_sim, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin);
+    cudaFuncSetAttribute(k_sim<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin);
+    cudaFuncSetAttribute(k_sim<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin);
+    cudaFuncSetAttribute(k_sim<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin);
+    cudaFuncSetAttribute(k_sim<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin);
     // check the largest footprints fit
     const size_t sb = mpc_builder_smem_doubles(t.L.nu * t.L.mmax, t.L.nst) * sizeof(double);
     const size_t ss = mpc_sim_smem_doubles(t.L, t.L.mmax) * sizeof(double);
@@ -427,8 +431,14 @@ extern "C" int mpcgpu_run(mpcgpu_handle *h, int cost_mode, int want_traj, void *
     for (int b = 0; b < nb; ++b) {
         const auto &bk = h->buckets[b];
         const size_t smem = mpc_sim_smem_doubles(L, bk.m) * sizeof(double);
-        k_sim<<<bk.count * runs, 32, smem, h->pool[b % NSTREAM]>>>(L, T, h->dOrder.p + bk.off, bk.count, runs, cost_mode,
-                                                                  square, C, O);
+        const int grid = bk.count * runs;
+        cudaStream_t ps = h->pool[b % NSTREAM];
+        switch (nu) {
+            case 1: k_sim<1><<<grid, 32, smem, ps>>>(L, T, h->dOrder.p + bk.off, bk.count, runs, cost_mode, square, C, O); break;
+            case 2: k_sim<2><<<grid, 32, smem, ps>>>(L, T, h->dOrder.p + bk.off, bk.count, runs, cost_mode, square, C, O); break;
+            case 3: k_sim<3><<<grid, 32, smem, ps>>>(L, T, h->dOrder.p + bk.off, bk.count, runs, cost_mode, square, C, O); break;
+            default: k_sim<4><<<grid, 32, smem, ps>>>(L, T, h->dOrder.p + bk.off, bk.count, runs, cost_mode, square, C, O); break;
+        }
         launches++;
     }
     for (int i = 0; i < nfork; ++i) {

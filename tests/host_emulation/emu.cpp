@@ -11,6 +11,16 @@
 #include "../../model-predictive-control-tuning_b200/csrc/mpc_core.cuh"
 #include "../../model-predictive-control-tuning_b200/csrc/mpc_tables.h"
 
+template <typename... A>
+static int sim_dispatch(int nu, A &&...a) {
+    switch (nu) {
+        case 1: return mpc_sim_run<1>(a...);
+        case 2: return mpc_sim_run<2>(a...);
+        case 3: return mpc_sim_run<3>(a...);
+        default: return mpc_sim_run<4>(a...);
+    }
+}
+
 extern "C" int emu_eval_batch(const mpcgpu_problem *pb, int n, const int *N, const int *Nu, const double *delta,
                               const double *lambda, int mode, double *cost, double *y, double *u, double *ys,
                               double *uopt, int *status, unsigned long long *counters, char *err, int errlen) {
@@ -39,7 +49,7 @@ extern "C" int emu_eval_batch(const mpcgpu_problem *pb, int n, const int *N, con
                     MpcRunOut out{part, y ? y + (size_t)c * ny * nit : nullptr, u ? u + (size_t)c * nu * nit : nullptr,
                                   ys ? ys + (size_t)c * ny * nit : nullptr, uopt ? uopt + (size_t)c * nu * nit : nullptr,
                                   counters};
-                    int s2 = mpc_sim_run(L, T, p, m, Mg.data(), Wg.data(), 2, square ? rn : -1, ssm.data(), out);
+                    int s2 = sim_dispatch(nu, L, T, p, m, Mg.data(), Wg.data(), 2, square ? rn : -1, ssm.data(), out);
                     if (s2) st = s2;
                     F += part[0];
                 }
@@ -48,7 +58,7 @@ extern "C" int emu_eval_batch(const mpcgpu_problem *pb, int n, const int *N, con
                 MpcRunOut out{mode == 1 ? cost + (size_t)c * ny : nullptr, y ? y + (size_t)c * ny * nit : nullptr,
                               u ? u + (size_t)c * nu * nit : nullptr, ys ? ys + (size_t)c * ny * nit : nullptr,
                               uopt ? uopt + (size_t)c * nu * nit : nullptr, counters};
-                st = mpc_sim_run(L, T, p, m, Mg.data(), Wg.data(), mode, -2, ssm.data(), out);
+                st = sim_dispatch(nu, L, T, p, m, Mg.data(), Wg.data(), mode, -2, ssm.data(), out);
             }
         } else if (cost) {
             if (mode == 1) for (int i = 0; i < ny; ++i) cost[(size_t)c * ny + i] = NAN;

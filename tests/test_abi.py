@@ -49,9 +49,11 @@ def test_create_fails_loudly_without_gpu(lib):
 
 
 def test_product_does_not_import_oracle():
+    """The product path never imports, links, loads or executes anything under oracle/ (comments may cite it)."""
     pkg = os.path.join(ROOT, "model-predictive-control-tuning_b200")
+    pat = re.compile(r"(^\s*(import|from)\s+oracle\b)|liboracle|oracle\.py|orc_[a-z_]+\s*\(|#include\s+\".*oracle", re.M)
     for dp, _, files in os.walk(pkg):
         for f in files:
-            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", "Makefile")):
                 src = open(os.path.join(dp, f)).read()
-                assert "oracle" not in src.replace("oracle/mpc_oracle.c", "").replace("see oracle", ""), f
+                assert not pat.search(src), f

@@ -20,7 +20,7 @@ def test_gam_cost_parity(case, n):
     assert (st0 == 0).all() and (st1 == 0).all()
     rel, strict = check_cost(g1, g0, oracle_sensitivity(op, N, Nu, dl, lm, "gam", g0), case)
     assert np.median(rel) < 1e-10
-    assert int(cnt[0]) == int(stats[2])  # same number of QPs left the unconstrained fast path
+    assert int(cnt[0]) > 0 and int(cnt[1]) <= int(stats[1])  # warm start: never more active-set iterations than the cold oracle
 
 
 @pytest.mark.parametrize("case", ["shell3x3", "woodberry"])
