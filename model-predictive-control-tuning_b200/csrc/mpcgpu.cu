@@ -20,7 +20,7 @@
 #include "mpc_core.cuh"
 #include "mpc_tables.h"
 
-#define NSTREAM 4
+#define NSTREAM 16  /* >= number of size buckets (mmax = 15): every bucket runs concurrently */
 #define BUILD_THREADS 128
 
 static std::string g_create_error;
