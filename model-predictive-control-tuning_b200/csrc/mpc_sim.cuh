@@ -1,0 +1,717 @@
+// mpc_sim.cuh -- the closed-loop kernel body: one warp runs one closed-loop simulation
+// (closedloop_toolbox.m:50-100 fused with the GAM / VNS cost sums), SIMT style.
+//
+// Row layout.  The decision vector is padded input-major: row r = j*P + c (input j, horizon index c),
+// P = 4, 8 or 16 >= m, R = NU*P rows, rows with c >= m are inert (zero rows of M and W, infinite bounds).
+// Lane l owns row l (slot 0) and row 32+l (slot 1, only when R = 48/64); everything indexed by row --
+// the QP iterate z, its bounds, W n, the step direction, the active-constraint mask -- lives in that
+// lane's REGISTERS.  The cumulative sums u(k+c) = u(k-1) + sum_{c'<=c} dz are segmented warp scans
+// (width P) instead of loops.  Shared memory holds M (read every sample), the physical plant state with
+// circular input histories, and the active-set factor:
+//     Li : inverse Cholesky factor of the Schur complement S = N'WN (W = H^-1, N = active normals)
+//     V  : V = W N Li'  (R x q).  With it   z = z_unc + V (Li g)   and the Goldfarb-Idnani step direction
+//          W (n_p - N r) = W n_p - V (Li N'W n_p)   cost O(R q) from shared memory instead of an R^2 pass
+//          over W in L2; the new column when p is added is dir/sqrt(rho), i.e. free.
+// Only the first QC active constraints keep V/Li in shared memory, the rest spill to a per-run global
+// scratch (rare: > 16 simultaneously active constraints).
+//
+// The algorithm (warm-started dual active set, tolerances, deviation coordinates) is the one validated
+// against the oracle; see DESIGN.md.  This header is also compiled by tests/host_emulation (thread-per-
+// lane emulation of the warp intrinsics) so that the not-gpu tests run the same source.
+#pragma once
+#include <math.h>
+
+#include "mpc_layout.h"
+
+#define SIM_VIOL_TOL 1e-10
+#define SIM_DEP_TOL 1e-13
+#define SIM_CH 32 /* samples of r / yref / v staged into shared memory at a time */
+#define SIM_INF (__builtin_huge_val())
+#define SIM_FULL 0xffffffffu
+
+struct MpcRunOut {
+    double *cost;                  // GAM: ny slots; VNS: 1 slot (partial sum of this run); RAW: nullptr
+    double *y, *u, *ys, *uopt;     // trajectories of this candidate (signals x nit) or nullptr
+    unsigned long long *counters;  // [0] constrained QPs, [1] active-set iterations
+};
+
+static MPC_HD int sim_pad(int m) { return m <= 4 ? 4 : (m <= 8 ? 8 : 16); }
+static MPC_HD int sim_qc(int R) { return R <= 24 ? R : 16; }
+static MPC_HD int sim_hl(const MpcLayout &L) {
+    int h = 1;
+    for (int j = 0; j < L.nw; ++j) h = L.hlen[j] > h ? L.hlen[j] : h;
+    return h + 1;
+}
+// per-run global scratch (doubles) for V columns / Li rows beyond QC
+static MPC_HD size_t sim_scratch_doubles(int R) {
+    const int qc = sim_qc(R);
+    return (size_t)(R - qc) * R + ((size_t)R * (R + 1) / 2 - (size_t)qc * (qc + 1) / 2);
+}
+static MPC_HD size_t sim_smem_doubles(const MpcLayout &L, int nu, int P) {
+    const int R = nu * P, qc = sim_qc(R), nch = L.ny * L.nw, HL = sim_hl(L);
+    size_t n = (size_t)L.nst * R;            // M
+    n += (L.nst + 1) & ~1;                    // st
+    n += 2 * nch;                             // x, xol
+    n += (size_t)L.nw * HL;                   // hist
+    n += 4 * nch;                             // cha, chb0, chb1, chg
+    n += (size_t)SIM_CH * (2 * L.ny + L.nd);  // sig
+    n += (size_t)nu * P;                      // uopt
+    n += 4 * nu;                              // bnd
+    n += 4 * (size_t)R;                       // z, lvl, w, w2
+    n += 4 * (size_t)R;                       // g, l, rr, mu
+    n += (size_t)qc * R + (size_t)qc * (qc + 1) / 2;  // V, Li
+    n += (2 * nch + L.nst + 2 * R + 8 + 1) / 2 + 1;   // ints: chd, chj, role, act, dflag, misc
+    return n;
+}
+
+struct SimSm {
+    double *M, *st, *x, *xol, *hist, *cha, *chb0, *chb1, *chg, *sig, *uopt, *bnd, *z, *lvl, *w, *w2, *g, *l, *rr, *mu, *V, *Li;
+    int *chd, *chj, *role, *act, *dflag, *misc;
+};
+
+__device__ __forceinline__ double sim_wsum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(SIM_FULL, v, o);
+    return v;
+}
+__device__ __forceinline__ double sim_wmax(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(SIM_FULL, v, o));
+    return v;
+}
+// all lanes end with the minimum value and, among equal values, the smallest non-negative index
+__device__ __forceinline__ void sim_wargmin(double &v, int &i) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(SIM_FULL, v, o);
+        const int oi = __shfl_xor_sync(SIM_FULL, i, o);
+        if (ov < v || (ov == v && oi >= 0 && (i < 0 || oi < i))) { v = ov; i = oi; }
+    }
+}
+
+template <int NU>
+__device__ __forceinline__ double sim_pick(const double (&u)[NU], int j) {
+    double r = u[0];
+#pragma unroll
+    for (int k = 1; k < NU; ++k) r = (j == k) ? u[k] : r;
+    return r;
+}
+
+// Everything one warp needs to carry through the run; template so that R, P, NSLOT are constants.
+template <int NU, int P>
+struct SimWarp {
+    static constexpr int R = NU * P;
+    static constexpr int NSLOT = (R + 31) / 32;
+    static constexpr int QC = (R <= 24) ? R : 16;
+    static constexpr int LI_SM = QC * (QC + 1) / 2;
+
+    const MpcLayout &L;
+    SimSm sm;
+    double *gscr;   // per-run global scratch (V columns / Li rows beyond QC), may be nullptr when QC == R
+    const double *W;
+    int lane, m;
+    // per-lane row data
+    int row[NSLOT];
+    bool valid[NSLOT];
+    double dlo[NSLOT], dhi[NSLOT], ulo[NSLOT], uhi[NSLOT];
+    double z[NSLOT];
+    int amask[NSLOT];
+    double u[NU];   // uniform: MV levels u(k-1)
+    int q;          // uniform: carried active-set size
+    unsigned long long n_con, n_it;
+
+    __device__ __forceinline__ SimWarp(const MpcLayout &L_) : L(L_) {}
+
+    __device__ __forceinline__ double *Vcol(int a) const { return a < QC ? sm.V + (size_t)a * R : gscr + (size_t)(a - QC) * R; }
+    __device__ __forceinline__ double *Lirow(int a) const {
+        return a < QC ? sm.Li + (a * (a + 1)) / 2 : gscr + (size_t)(R - QC) * R + ((a * (a + 1)) / 2 - LI_SM);
+    }
+
+    // u(k+c) for this lane's rows: u_j(k-1) + inclusive scan of z over c within the input's segment
+    __device__ __forceinline__ void levels(double (&lv)[NSLOT]) const {
+#pragma unroll
+        for (int s = 0; s < NSLOT; ++s) {
+            double v = z[s];
+            const int c = row[s] & (P - 1);
+#pragma unroll
+            for (int off = 1; off < P; off <<= 1) {
+                const double t = __shfl_up_sync(SIM_FULL, v, off, P);
+                if (c >= off) v += t;
+            }
+            lv[s] = sim_pick<NU>(u, (row[s] / P) < NU ? (row[s] / P) : 0) + v;
+        }
+    }
+    __device__ __forceinline__ void publish(const double (&lv)[NSLOT]) const {
+#pragma unroll
+        for (int s = 0; s < NSLOT; ++s)
+            if (row[s] < R) { sm.z[row[s]] = z[s]; sm.lvl[row[s]] = lv[s]; }
+        __syncwarp();
+    }
+    // slack of constraint cid from the published z / lvl (any lane)
+    __device__ __forceinline__ double slack_of(int cid) const {
+        const int type = cid & 3, r = cid >> 2, j = r / P;
+        const double *b = sm.bnd + 4 * j;  // dumin, dumax, umin, umax
+        switch (type) {
+            case 0: return sm.z[r] - b[0];
+            case 1: return b[1] - sm.z[r];
+            case 2: return sm.lvl[r] - b[2];
+            default: return b[3] - sm.lvl[r];
+        }
+    }
+    // n_cid' x for a published row vector x (shared memory)
+    __device__ __forceinline__ double ndot(int cid, const double *x) const {
+        const int type = cid & 3, r = cid >> 2;
+        if (type < 2) return type == 0 ? x[r] : -x[r];
+        const int base = r & ~(P - 1), c = r & (P - 1);
+        double acc = 0.0;
+        for (int c2 = 0; c2 <= c; ++c2) acc += x[base + c2];
+        return type == 2 ? acc : -acc;
+    }
+    // wv = W n_cid for this lane's rows (W symmetric: rows read coalesced); also published to dst
+    __device__ __forceinline__ void w_times_normal(int cid, double (&wv)[NSLOT], double *dst) const {
+        const int type = cid & 3, r = cid >> 2;
+        const double sg = (type == 0 || type == 2) ? 1.0 : -1.0;
+#pragma unroll
+        for (int s = 0; s < NSLOT; ++s) {
+            double acc = 0.0;
+            if (row[s] < R) {
+                if (type < 2) {
+                    acc = W[(size_t)r * R + row[s]];
+                } else {
+                    const int base = r & ~(P - 1), c = r & (P - 1);
+#pragma unroll 4
+                    for (int c2 = 0; c2 <= c; ++c2) acc += W[(size_t)(base + c2) * R + row[s]];
+                }
+                acc *= sg;
+                dst[row[s]] = acc;
+            }
+            wv[s] = acc;
+        }
+        __syncwarp();
+    }
+    // g = N' x (x published), l = Li g, rr = Li' l for the first qq active constraints; returns |l|^2
+    __device__ __forceinline__ double schur_vectors(int qq, const double *x) const {
+        for (int a = lane; a < qq; a += 32) sm.g[a] = ndot(sm.act[a], x);
+        __syncwarp();
+        double part = 0.0;
+        for (int a = lane; a < qq; a += 32) {
+            const double *row_a = Lirow(a);
+            double acc = 0.0;
+            for (int b = 0; b <= a; ++b) acc += row_a[b] * sm.g[b];
+            sm.l[a] = acc;
+            part += acc * acc;
+        }
+        const double l2 = sim_wsum(part);
+        __syncwarp();
+        for (int a = lane; a < qq; a += 32) {
+            double acc = 0.0;
+            for (int b = a; b < qq; ++b) acc += Lirow(b)[a] * sm.l[b];
+            sm.rr[a] = acc;
+        }
+        __syncwarp();
+        return l2;
+    }
+    // l = Li g, mu_out = Li' l  (g already in sm.g)
+    __device__ __forceinline__ void schur_solve(int qq, double *mu_out) const {
+        for (int a = lane; a < qq; a += 32) {
+            const double *row_a = Lirow(a);
+            double acc = 0.0;
+            for (int b = 0; b <= a; ++b) acc += row_a[b] * sm.g[b];
+            sm.l[a] = acc;
+        }
+        __syncwarp();
+        for (int a = lane; a < qq; a += 32) {
+            double acc = 0.0;
+            for (int b = a; b < qq; ++b) acc += Lirow(b)[a] * sm.l[b];
+            mu_out[a] = acc;
+        }
+        __syncwarp();
+    }
+    // x_rows -= / += sum_a coef[a] * V_a   (per-lane rows)
+    __device__ __forceinline__ void add_V(int qq, const double *coef, double sign, double (&x)[NSLOT]) const {
+        for (int a = 0; a < qq; ++a) {
+            const double ca = sign * coef[a];
+            const double *va = Vcol(a);
+#pragma unroll
+            for (int s = 0; s < NSLOT; ++s)
+                if (row[s] < R) x[s] += ca * va[row[s]];
+        }
+    }
+    // commit constraint cid at position a: V_a = dir / sqrt(rho), Li row a = [-rr'/sqrt(rho), 1/sqrt(rho)]
+    __device__ __forceinline__ void commit(int cid, int a, double rho, double mu_new, const double (&dir)[NSLOT]) {
+        const double isr = 1.0 / sqrt(rho);
+        double *va = Vcol(a), *lr = Lirow(a);
+#pragma unroll
+        for (int s = 0; s < NSLOT; ++s)
+            if (row[s] < R) va[row[s]] = dir[s] * isr;
+        for (int b = lane; b < a; b += 32) lr[b] = -sm.rr[b] * isr;
+        if (lane == 0) { lr[a] = isr; sm.act[a] = cid; sm.mu[a] = mu_new; }
+#pragma unroll
+        for (int s = 0; s < NSLOT; ++s)
+            if (row[s] == (cid >> 2)) amask[s] |= (1 << (cid & 3));
+        __syncwarp();
+    }
+    // remove the active constraints flagged in sm.dflag (order of the rest kept), rebuild V / Li behind
+    __device__ __forceinline__ void drop_flagged() {
+        for (int a = 0; a < q; ++a) {  // clear mask bits (uniform loop)
+            if (sm.dflag[a]) {
+                const int cid = sm.act[a];
+#pragma unroll
+                for (int s = 0; s < NSLOT; ++s)
+                    if (row[s] == (cid >> 2)) amask[s] &= ~(1 << (cid & 3));
+            }
+        }
+        __syncwarp();
+        if (lane == 0) {
+            int qn = 0, first = -1;
+            for (int a = 0; a < q; ++a) {
+                if (sm.dflag[a]) { if (first < 0) first = a; }
+                else { sm.act[qn] = sm.act[a]; sm.mu[qn] = sm.mu[a]; ++qn; }
+            }
+            sm.misc[0] = qn; sm.misc[1] = first < 0 ? qn : first;
+        }
+        __syncwarp();
+        const int qn = sm.misc[0], first = sm.misc[1];
+        __syncwarp();
+        for (int a = first; a < qn; ++a) {
+            const int cid = sm.act[a];
+            const double mua = sm.mu[a];
+            double wv[NSLOT];
+            w_times_normal(cid, wv, sm.w2);
+            const double gam = ndot(cid, sm.w2);
+            const double l2 = schur_vectors(a, sm.w2);
+            double rho = gam - l2;
+            if (!(rho > 0.0)) rho = SIM_DEP_TOL * gam;
+            add_V(a, sm.l, -1.0, wv);
+            commit(cid, a, rho, mua, wv);
+        }
+        q = qn;
+    }
+
+    // Dual active-set QP, warm-started from the carried set.  z (registers) in: z_unc, out: optimum.
+    __device__ __forceinline__ int qp_solve() {
+        int it = 0;
+        const int itmax = 20 * (NU * m + 10);
+        double lv[NSLOT];
+        // ---- warm start on the carried set: mu = S^-1 (b_A - N_A' z_unc), shed negative multipliers ----
+        while (q > 0) {
+            levels(lv);
+            publish(lv);
+            for (int a = lane; a < q; a += 32) sm.g[a] = -slack_of(sm.act[a]);
+            __syncwarp();
+            schur_solve(q, sm.mu);
+            double mumax = 0.0;
+            for (int a = lane; a < q; a += 32) mumax = fmax(mumax, fabs(sm.mu[a]));
+            mumax = sim_wmax(mumax);
+            int nd_ = 0;
+            for (int a = lane; a < q; a += 32) {
+                const int fl = sm.mu[a] < -1e-12 * mumax;
+                sm.dflag[a] = fl;
+                nd_ |= fl;
+            }
+            nd_ = __any_sync(SIM_FULL, nd_);
+            __syncwarp();
+            if (!nd_) break;
+            it += 1;
+            drop_flagged();
+        }
+        if (q > 0) {  // z = z_unc + V l  (l = Li g is still in sm.l)
+            add_V(q, sm.l, 1.0, z);
+            for (int a = lane; a < q; a += 32) if (sm.mu[a] < 0.0) sm.mu[a] = 0.0;
+            __syncwarp();
+        }
+        // ---- Goldfarb-Idnani iterations ----
+        for (;;) {
+            levels(lv);
+            double bv = -SIM_VIOL_TOL;
+            int bi = -1;
+#pragma unroll
+            for (int s = 0; s < NSLOT; ++s) {
+                if (!valid[s]) continue;
+                const double sl[4] = {z[s] - dlo[s], dhi[s] - z[s], lv[s] - ulo[s], uhi[s] - lv[s]};
+#pragma unroll
+                for (int type = 0; type < 4; ++type) {
+                    if (amask[s] & (1 << type)) continue;
+                    const int id = type | (row[s] << 2);
+                    if (sl[type] < bv || (sl[type] == bv && bi >= 0 && id < bi)) { bv = sl[type]; bi = id; }
+                }
+            }
+            sim_wargmin(bv, bi);
+            if (bi < 0) break;
+            const int p = bi;
+            double sp = bv, mu_p = 0.0;
+            double wv[NSLOT];
+            w_times_normal(p, wv, sm.w);
+            const double gamma = ndot(p, sm.w);
+            for (;;) {
+                if (++it > itmax) { n_it += it; return 2; }
+                const double l2 = schur_vectors(q, sm.w);
+                const double rho = gamma - l2;
+                const int dependent = !(rho > SIM_DEP_TOL * gamma);
+                double t1 = SIM_INF;
+                int l1 = -1;
+                for (int a = lane; a < q; a += 32) {
+                    const double ra = sm.rr[a];
+                    if (ra > 0.0) {
+                        const double t = sm.mu[a] / ra;
+                        if (t < t1 || (t == t1 && l1 >= 0 && a < l1)) { t1 = t; l1 = a; }
+                    }
+                }
+                sim_wargmin(t1, l1);
+                const double t2 = dependent ? SIM_INF : -sp / rho;
+                const double t = t1 < t2 ? t1 : t2;
+                if (!(t < SIM_INF)) { n_it += it; return 1; }
+                const int full = !(dependent || t1 < t2);
+                double dir[NSLOT];
+#pragma unroll
+                for (int s = 0; s < NSLOT; ++s) dir[s] = wv[s];
+                if (!dependent) {  // primal step along dir = W n_p - V l
+                    add_V(q, sm.l, -1.0, dir);
+#pragma unroll
+                    for (int s = 0; s < NSLOT; ++s) z[s] += t * dir[s];
+                    sp += t * rho;
+                }
+                for (int a = lane; a < q; a += 32) {
+                    sm.mu[a] -= t * sm.rr[a];
+                    sm.dflag[a] = (a == l1) && !full;
+                }
+                mu_p += t;
+                __syncwarp();
+                if (full) {
+                    commit(p, q, rho, mu_p, dir);
+                    q += 1;
+                    break;
+                }
+                drop_flagged();
+            }
+        }
+        // ---- one Newton correction on the active constraints if they drifted: z += V Li (-slack_A) ----
+        if (q > 0) {
+            publish(lv);
+            double worst = 0.0;
+            for (int a = lane; a < q; a += 32) {
+                const double sl = slack_of(sm.act[a]);
+                sm.g[a] = -sl;
+                worst = fmax(worst, fabs(sl));
+            }
+            worst = sim_wmax(worst);
+            __syncwarp();
+            if (worst > 1e-13) {
+                for (int a = lane; a < q; a += 32) {
+                    const double *row_a = Lirow(a);
+                    double acc = 0.0;
+                    for (int b = 0; b <= a; ++b) acc += row_a[b] * sm.g[b];
+                    sm.l[a] = acc;
+                }
+                __syncwarp();
+                add_V(q, sm.l, 1.0, z);
+                __syncwarp();
+            }
+        }
+        n_it += it;
+        return 0;
+    }
+
+    // z = M st (st already in shared memory), box/rate check, QP if needed.
+    __device__ __forceinline__ int controller_move() {
+        const int nst = L.nst;
+#pragma unroll
+        for (int s = 0; s < NSLOT; ++s) z[s] = 0.0;
+        {
+            double acc0[NSLOT], acc1[NSLOT];
+#pragma unroll
+            for (int s = 0; s < NSLOT; ++s) { acc0[s] = 0.0; acc1[s] = 0.0; }
+            int sg = 0;
+#pragma unroll 2
+            for (; sg + 1 < nst; sg += 2) {
+                const double s0 = sm.st[sg], s1 = sm.st[sg + 1];
+#pragma unroll
+                for (int s = 0; s < NSLOT; ++s)
+                    if (row[s] < R) {
+                        acc0[s] = fma(sm.M[(size_t)sg * R + row[s]], s0, acc0[s]);
+                        acc1[s] = fma(sm.M[(size_t)(sg + 1) * R + row[s]], s1, acc1[s]);
+                    }
+            }
+            if (sg < nst) {
+                const double s0 = sm.st[sg];
+#pragma unroll
+                for (int s = 0; s < NSLOT; ++s)
+                    if (row[s] < R) acc0[s] = fma(sm.M[(size_t)sg * R + row[s]], s0, acc0[s]);
+            }
+#pragma unroll
+            for (int s = 0; s < NSLOT; ++s) z[s] = acc0[s] + acc1[s];
+        }
+        if (q == 0) {
+            double lv[NSLOT];
+            levels(lv);
+            int bad = 0;
+#pragma unroll
+            for (int s = 0; s < NSLOT; ++s)
+                if (valid[s])
+                    bad |= (z[s] - dlo[s] < -SIM_VIOL_TOL) | (dhi[s] - z[s] < -SIM_VIOL_TOL) |
+                           (lv[s] - ulo[s] < -SIM_VIOL_TOL) | (uhi[s] - lv[s] < -SIM_VIOL_TOL);
+            if (!__any_sync(SIM_FULL, bad)) return 0;
+        }
+        n_con += 1;
+        return qp_solve();
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// One closed-loop run.  sel: -2 user set-point (GAM / RAW); -1 VNS unit step on every output;
+// i >= 0 VNS unit step on output i only (VNS2.m:148-165).  mode: 0 RAW, 1 GAM, 2 VNS.
+// Mg: nst x R (row-padded, [col][row]); Wg: R x R.
+// ------------------------------------------------------------------------------------------------
+template <int NU, int P>
+__device__ __forceinline__ int sim_run(const MpcLayout &L, const MpcTables &T, int m, const double *__restrict__ Mg,
+                                       const double *__restrict__ Wg, int mode, int sel, double *smem, double *gscr,
+                                       const MpcRunOut &out) {
+    constexpr int R = NU * P;
+    constexpr int NSLOT = (R + 31) / 32;
+    constexpr int QC = (R <= 24) ? R : 16;
+    const int lane = threadIdx.x & 31;
+    const int ny = L.ny, nd = L.nd, nw = L.nw, nch = ny * nw, nst = L.nst, nit = L.nit;
+    const int HL = sim_hl(L);
+    const int nsig = 2 * ny + nd;
+    SimWarp<NU, P> wp(L);
+    SimSm &sm = wp.sm;
+    {   // carve shared memory
+        double *p = smem;
+        sm.M = p; p += (size_t)nst * R;
+        sm.st = p; p += (nst + 1) & ~1;
+        sm.x = p; p += nch;
+        sm.xol = p; p += nch;
+        sm.hist = p; p += (size_t)nw * HL;
+        sm.cha = p; p += nch; sm.chb0 = p; p += nch; sm.chb1 = p; p += nch; sm.chg = p; p += nch;
+        sm.sig = p; p += (size_t)SIM_CH * nsig;
+        sm.uopt = p; p += NU * P;
+        sm.bnd = p; p += 4 * NU;
+        sm.z = p; p += R; sm.lvl = p; p += R; sm.w = p; p += R; sm.w2 = p; p += R;
+        sm.g = p; p += R; sm.l = p; p += R; sm.rr = p; p += R; sm.mu = p; p += R;
+        sm.V = p; p += (size_t)QC * R;
+        sm.Li = p; p += (size_t)QC * (QC + 1) / 2;
+        int *ip = (int *)p;
+        sm.chd = ip; ip += nch; sm.chj = ip; ip += nch; sm.role = ip; ip += nst;
+        sm.act = ip; ip += R; sm.dflag = ip; ip += R; sm.misc = ip;
+    }
+    wp.gscr = gscr; wp.W = Wg; wp.lane = lane; wp.m = m; wp.q = 0; wp.n_con = 0; wp.n_it = 0;
+#pragma unroll
+    for (int s = 0; s < NSLOT; ++s) {
+        const int r = s * 32 + lane;
+        const int j = r / P, c = r & (P - 1);
+        wp.row[s] = r;
+        wp.valid[s] = (r < R) && (c < m);
+        const int jj = j < NU ? j : 0;
+        wp.dlo[s] = wp.valid[s] ? L.dumin[jj] : -SIM_INF;
+        wp.dhi[s] = wp.valid[s] ? L.dumax[jj] : SIM_INF;
+        wp.ulo[s] = wp.valid[s] ? L.umin[jj] : -SIM_INF;
+        wp.uhi[s] = wp.valid[s] ? L.umax[jj] : SIM_INF;
+        wp.z[s] = 0.0;
+        wp.amask[s] = 0;
+    }
+#pragma unroll
+    for (int j = 0; j < NU; ++j) wp.u[j] = 0.0;
+    // ---- one-time staging ----
+    for (int i = lane; i < nst * R; i += 32) sm.M[i] = Mg[i];
+    for (int ch = lane; ch < nch; ch += 32) {
+        sm.cha[ch] = L.a[ch]; sm.chb0[ch] = L.b0[ch]; sm.chb1[ch] = L.b1[ch]; sm.chg[ch] = L.gain[ch];
+        sm.chd[ch] = L.d[ch]; sm.chj[ch] = ch % nw;
+        sm.x[ch] = 0.0; sm.xol[ch] = 0.0;
+    }
+    for (int i = lane; i < nw * HL; i += 32) sm.hist[i] = 0.0;
+    for (int i = lane; i < NU * P; i += 32) sm.uopt[i] = 0.0;
+    for (int j = lane; j < NU; j += 32) {
+        sm.bnd[4 * j + 0] = L.dumin[j]; sm.bnd[4 * j + 1] = L.dumax[j]; sm.bnd[4 * j + 2] = L.umin[j]; sm.bnd[4 * j + 3] = L.umax[j];
+    }
+    // role of every deviation coordinate: kind | a << 2 | b << 12  (kind 0: x_ch, 1: hist(j=a, lag=b), 2: e_i)
+    for (int col = lane; col < nst; col += 32) {
+        int role;
+        if (col < nch) role = 0 | (col << 2);
+        else if (col >= L.stoff_e) role = 2 | ((col - L.stoff_e) << 2);
+        else {
+            int j = 0;
+            while (j + 1 < nw && col >= L.stoff_h[j + 1]) ++j;
+            role = 1 | (j << 2) | ((L.hq0[j] + (col - L.stoff_h[j])) << 12);
+        }
+        sm.role[col] = role;
+    }
+    __syncwarp();
+    int head = 0;   // uniform: physical slot of lag 0 in every circular history
+    int status = 0;
+    const bool want_ol = (mode != 1) || out.ys || out.uopt;
+    double jnu = 0.0;
+    double cost_acc = 0.0;  // per lane: lane i < ny accumulates output i
+
+    // set-point of output i at sample k for this run
+    auto setpoint = [&](int i, int k, double r_user) -> double {
+        if (sel == -2) return r_user;
+        return (sel == -1 || sel == i) ? (k >= L.inK - 1 ? 1.0 : 0.0) : 0.0;
+    };
+    // build st from the physical state; hv_md / r taken from `sigrow` (r at [0,ny), yref [ny,2ny), v [2ny,..))
+    auto build_st = [&](const double *sigrow, int k, bool do_cost) {
+        for (int col = lane; col < nst; col += 32) {
+            const int role = sm.role[col];
+            const int kind = role & 3, a = (role >> 2) & 1023, b = role >> 12;
+            double val;
+            if (kind == 0) {
+                const int j = sm.chj[a];
+                const double hv = j < NU ? sim_pick<NU>(wp.u, j) : sigrow[2 * ny + (j - NU)];
+                val = sm.x[a] - sm.chg[a] * hv;
+            } else if (kind == 1) {
+                const int j = a;
+                const double hv = j < NU ? sim_pick<NU>(wp.u, j) : sigrow[2 * ny + (j - NU)];
+                int pos = head + b;
+                if (pos >= HL) pos -= HL;
+                val = sm.hist[j * HL + pos] - hv;
+            } else {
+                const int i = a;
+                double yi = 0.0, ysi = 0.0, gsum = 0.0;
+                for (int j = 0; j < nw; ++j) {
+                    yi += sm.x[i * nw + j];
+                    ysi += sm.xol[i * nw + j];
+                    const double hv = j < NU ? sim_pick<NU>(wp.u, j) : sigrow[2 * ny + (j - NU)];
+                    gsum += sm.chg[i * nw + j] * hv;
+                }
+                val = setpoint(i, k, sigrow[i]) - gsum;
+                if (do_cost) {
+                    const bool mine = (sel < 0 || sel == i);
+                    if (out.y && mine) out.y[(size_t)i * nit + k] = yi;
+                    if (out.ys && mine) out.ys[(size_t)i * nit + k] = ysi;
+                    if (mode == 1) {
+                        const double e = yi - sigrow[ny + i];
+                        cost_acc += e * e;
+                    } else if (mode == 2 && k >= L.inK - 1 && mine) {
+                        const double e2 = yi - ysi, er = yi - sigrow[ny + i];
+                        cost_acc += e2 * e2 + er * er;
+                    }
+                }
+            }
+            sm.st[col] = val;
+        }
+        __syncwarp();
+    };
+    auto stage_signals = [&](int k0) {
+        const int cnt = (nit - k0) < SIM_CH ? (nit - k0) : SIM_CH;
+        for (int idx = lane; idx < cnt * nsig; idx += 32) {
+            const int kk = idx / nsig, c = idx - kk * nsig;
+            double v;
+            if (c < ny) v = T.r[(size_t)(k0 + kk) * ny + c];
+            else if (c < 2 * ny) v = T.yref[(size_t)(c - ny) * nit + (k0 + kk)];
+            else v = T.v[(size_t)(k0 + kk) * nd + (c - 2 * ny)];
+            sm.sig[kk * nsig + c] = v;
+        }
+        __syncwarp();
+    };
+
+    // ---------------- open-loop optimum (closedloop_toolbox.m:85-98) ----------------
+    if (want_ol) {
+        // the fresh controller state: x = 0, histories 0, u(-1) = 0; r = last row, v = last row
+        if (lane < nsig) {
+            const int c = lane;
+            double v;
+            if (c < ny) v = T.r[(size_t)(nit - 1) * ny + c];
+            else if (c < 2 * ny) v = 0.0;
+            else v = T.v[(size_t)(nit - 1) * nd + (c - 2 * ny)];
+            sm.sig[c] = v;
+        }
+        __syncwarp();
+        build_st(sm.sig, nit - 1, false);
+        const int rc = wp.controller_move();
+        if (rc) status = rc;
+        // uopt levels: inclusive scan of z (u(-1) = 0)
+        double lv[NSLOT];
+        wp.levels(lv);
+#pragma unroll
+        for (int s = 0; s < NSLOT; ++s)
+            if (wp.row[s] < R) sm.uopt[wp.row[s]] = lv[s];   // [j*P + c]
+        __syncwarp();
+        if (mode == 2) {  // Jnu (VNS2.m:183-191)
+            double part = 0.0;
+            for (int j = lane; j < NU; j += 32) {
+                if (sel < 0 || sel == j) {
+                    const double u0 = fabs(sm.uopt[j * P]);
+                    for (int c = 0; c + 1 < m && c + 1 < nit; ++c) {
+                        const double df = fabs(sm.uopt[j * P + c + 1] - sm.uopt[j * P + c]);
+                        const double xn = u0 / df;
+                        if (fabs(xn) <= 1.7976931348623157e308) part += xn * xn;  // inf / nan -> 0 (VNS2.m:186)
+                    }
+                }
+            }
+            jnu = sim_wsum(part);
+        }
+        // the closed loop starts from an empty active set
+        wp.q = 0;
+#pragma unroll
+        for (int s = 0; s < NSLOT; ++s) wp.amask[s] = 0;
+        __syncwarp();
+    }
+    // ---------------- closed loop (:50) + open-loop rollout (:100) in lock-step ----------------
+    for (int k = 0; k < nit; ++k) {
+        if ((k & (SIM_CH - 1)) == 0) stage_signals(k);
+        const double *sigrow = sm.sig + (size_t)(k & (SIM_CH - 1)) * nsig;
+        build_st(sigrow, k, true);
+        const int rc = wp.controller_move();
+        if (rc) status = rc;
+        // apply the first move of every input
+#pragma unroll
+        for (int j = 0; j < NU; ++j) {
+            const int r0 = j * P;
+            const double du = __shfl_sync(SIM_FULL, wp.z[r0 >> 5], r0 & 31);
+            wp.u[j] += du;
+        }
+        if (lane < NU) {
+            const int j = lane;
+            const bool mine = (sel < 0 || sel == j);
+            if (out.u && mine) out.u[(size_t)j * nit + k] = sim_pick<NU>(wp.u, j);
+            if (out.uopt && mine) out.uopt[(size_t)j * nit + k] = sm.uopt[j * P + (k < m ? k : m - 1)];
+        }
+        // plant sample: x(k+1) = a x(k) + b0 w(k+1-d) + b1 w(k-d); lag q of the history is w(k-1-q)
+        for (int ch = lane; ch < nch; ch += 32) {
+            const int j = sm.chj[ch], dd = sm.chd[ch];
+            const double wk = j < NU ? sim_pick<NU>(wp.u, j) : sigrow[2 * ny + (j - NU)];
+            int p1 = head + (dd > 0 ? dd - 1 : 0); if (p1 >= HL) p1 -= HL;   // indices stay in range even
+            int p0 = head + (dd > 1 ? dd - 2 : 0); if (p0 >= HL) p0 -= HL;   // when the value is unused
+            const double w1 = dd == 0 ? wk : sm.hist[j * HL + p1];
+            const double w0 = dd == 0 ? 0.0 : (dd == 1 ? wk : sm.hist[j * HL + p0]);
+            sm.x[ch] = sm.cha[ch] * sm.x[ch] + sm.chb0[ch] * w0 + sm.chb1[ch] * w1;
+            if (want_ol) {
+                double o1, o0;
+                if (j < NU) {
+                    const int k1 = k - dd, k0 = k + 1 - dd;
+                    o1 = k1 < 0 ? 0.0 : sm.uopt[j * P + (k1 < m ? k1 : m - 1)];
+                    o0 = (dd == 0 || k0 < 0) ? 0.0 : sm.uopt[j * P + (k0 < m ? k0 : m - 1)];
+                } else {  // the measured disturbance is the same signal in both simulations
+                    o1 = w1; o0 = w0;
+                }
+                sm.xol[ch] = sm.cha[ch] * sm.xol[ch] + sm.chb0[ch] * o0 + sm.chb1[ch] * o1;
+            }
+        }
+        // push w(k): the slot being overwritten held lag HL-1, which nobody reads
+        const int nhead = head == 0 ? HL - 1 : head - 1;
+        if (lane < nw) {
+            const int j = lane;
+            sm.hist[j * HL + nhead] = j < NU ? sim_pick<NU>(wp.u, j) : sigrow[2 * ny + (j - NU)];
+        }
+        head = nhead;
+        __syncwarp();
+    }
+    // ---------------- costs ----------------
+    if (out.cost) {
+        if (mode == 1) {
+            // lane holding column stoff_e + i accumulated output i
+            for (int i = 0; i < ny; ++i) {
+                const int col = L.stoff_e + i;
+                const double ci = __shfl_sync(SIM_FULL, cost_acc, col & 31);
+                if (lane == 0) out.cost[i] = status ? NAN : ci;
+            }
+        } else if (mode == 2) {
+            const double tot = sim_wsum(cost_acc) + jnu;
+            if (lane == 0) out.cost[0] = status ? NAN : tot;
+        }
+    }
+    if (out.counters && lane == 0) {
+        atomicAdd(out.counters + 0, wp.n_con);
+        atomicAdd(out.counters + 1, wp.n_it);
+    }
+    return status;
+}

@@ -1,11 +1,10 @@
 // mpcgpu.cu -- kernels + C ABI of libmpcgpu.so (include/mpcgpu.h).  sm_100a only, no CPU fallback.
 //
 // Launch structure of one population evaluation (mpcgpu_run):
-//   candidates are bucketed on the host by control horizon m (the only size that fixes the shared-memory
-//   footprint nz = nu*m), largest m first, each bucket on its own forked stream:
-//     k_build : one CTA (128 threads) per candidate  -> M (nst x nz), W = H^-1 (nz x nz) in HBM
-//     k_sim   : one warp per closed-loop run; M staged into shared memory once,
-//               W read through L1/L2 only when a QP leaves the unconstrained fast path
+//   candidates are bucketed on the host by padded control horizon P = 4 / 8 / 16 >= m (it fixes the row
+//   count R = nu*P and with it the shared-memory footprint), largest first, each bucket on its own stream:
+//     k_build      : one CTA (128 threads) per candidate -> M (nst x R), W = H^-1 (R x R) in HBM
+//     k_sim<NU,P>  : one warp per closed-loop run (mpc_sim.cuh)
 //   k_finish  : VNS only, F = sum_runs partial + N
 #include <cuda_runtime.h>
 
@@ -18,9 +17,10 @@
 
 #include "../../include/mpcgpu.h"
 #include "mpc_core.cuh"
+#include "mpc_sim.cuh"
 #include "mpc_tables.h"
 
-#define NSTREAM 16  /* >= number of size buckets (mmax = 15): every bucket runs concurrently */
+#define NSTREAM 4  /* >= number of size buckets (P = 4, 8, 16): every bucket runs concurrently */
 #define BUILD_THREADS 128
 
 static std::string g_create_error;
@@ -42,6 +42,8 @@ struct DevCand {
     const long long *offM, *offW;
     double *M, *W;
     int *bstatus;  // builder status per candidate
+    double *scratch;  // per-run spill area of the closed-loop kernel (V / Li beyond QC)
+    long long scratch_stride;
 };
 
 struct DevOut {
@@ -67,16 +69,16 @@ __global__ void __launch_bounds__(BUILD_THREADS) k_build(const MpcLayout L, cons
 }
 
 // One warp per (candidate, run).  mode: 0 RAW, 1 GAM, 2 VNS.
-template <int NU>
+template <int NU, int P>
 __global__ void __launch_bounds__(32) k_sim(const MpcLayout L, const MpcTables T, const int *order, int count, int runs,
-                                            int mode, int square, DevCand C, DevOut O) {
+                                            int mode, int square, long long item0, DevCand C, DevOut O) {
     extern __shared__ double smem_s[];
     const int item = blockIdx.x;
     if (item >= count * runs) return;
     const int c = order[item / runs];
     const int run = item - (item / runs) * runs;
-    const int p = C.N[c], m = C.Nu[c];
-    const int ny = L.ny, nu = L.nu, nit = L.nit;
+    const int m = C.Nu[c];
+    const int ny = L.ny, nit = L.nit;
     if (C.bstatus[c] != 0) {
         if ((threadIdx.x & 31) == 0) {
             atomicMax(O.status + c, C.bstatus[c]);
@@ -88,13 +90,25 @@ __global__ void __launch_bounds__(32) k_sim(const MpcLayout L, const MpcTables T
     MpcRunOut out;
     out.cost = mode == 1 ? O.cost + (size_t)c * ny : (mode == 2 ? O.part + (size_t)c * runs + run : nullptr);
     out.y = O.y ? O.y + (size_t)c * ny * nit : nullptr;
-    out.u = O.u ? O.u + (size_t)c * nu * nit : nullptr;
+    out.u = O.u ? O.u + (size_t)c * NU * nit : nullptr;
     out.ys = O.ys ? O.ys + (size_t)c * ny * nit : nullptr;
-    out.uopt = O.uopt ? O.uopt + (size_t)c * nu * nit : nullptr;
+    out.uopt = O.uopt ? O.uopt + (size_t)c * NU * nit : nullptr;
     out.counters = O.counters;
     const int sel = mode == 2 ? (square ? run : -1) : -2;
-    const int st = mpc_sim_run<NU>(L, T, p, m, C.M + C.offM[c], C.W + C.offW[c], mode, sel, smem_s, out);
+    double *gscr = C.scratch ? C.scratch + (size_t)(item0 + item) * C.scratch_stride : nullptr;
+    const int st = sim_run<NU, P>(L, T, m, C.M + C.offM[c], C.W + C.offW[c], mode, sel, smem_s, gscr, out);
     if (st != 0 && (threadIdx.x & 31) == 0) atomicMax(O.status + c, st);
+}
+
+typedef void (*sim_kernel_t)(const MpcLayout, const MpcTables, const int *, int, int, int, int, long long, DevCand, DevOut);
+static sim_kernel_t sim_kernel(int nu, int P) {
+    switch (nu * 100 + P) {
+        case 104: return k_sim<1, 4>;   case 108: return k_sim<1, 8>;   case 116: return k_sim<1, 16>;
+        case 204: return k_sim<2, 4>;   case 208: return k_sim<2, 8>;   case 216: return k_sim<2, 16>;
+        case 304: return k_sim<3, 4>;   case 308: return k_sim<3, 8>;   case 316: return k_sim<3, 16>;
+        case 404: return k_sim<4, 4>;   case 408: return k_sim<4, 8>;   case 416: return k_sim<4, 16>;
+    }
+    return nullptr;
 }
 
 __global__ void k_finish_vns(int n, int runs, const int *N, const double *part, const int *status, double *cost) {
@@ -170,12 +184,12 @@ struct mpcgpu_handle {
     int last_mode = -1, last_traj = 0;
     std::vector<int> hN, hNu, hOrder, hInvalid;
     std::vector<long long> hOffM, hOffW;
-    struct Bucket { int m, off, count; };
+    struct Bucket { int P, mmax, off, count; };
     std::vector<Bucket> buckets;
     int n_valid = 0;
     DBuf<int> dN, dNu, dOrder, dInvalid, dBStatus, dStatus;
     DBuf<long long> dOffM, dOffW;
-    DBuf<double> dDelta, dLambda, dM, dW, dCost, dPart, dY, dU, dYs, dUopt;
+    DBuf<double> dDelta, dLambda, dM, dW, dCost, dPart, dY, dU, dYs, dUopt, dScratch;
     DBuf<unsigned long long> dCounters;
     HBuf<double> pinD, pinOut;
     HBuf<int> pinI;
@@ -259,13 +273,11 @@ extern "C" int mpcgpu_create(const mpcgpu_problem *problem, int device, mpcgpu_h
     if ((ce = h->dCounters.ensure(4)) != cudaSuccess) return fail("alloc counters", ce);
     // allow large dynamic shared memory on both kernels
     cudaFuncSetAttribute(k_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin);
-    cudaFuncSetAttribute(k_sim<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin);
-    cudaFuncSetAttribute(k_sim<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin);
-    cudaFuncSetAttribute(k_sim<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin);
-    cudaFuncSetAttribute(k_sim<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin);
+    for (int P = 4; P <= 16; P *= 2)
+        cudaFuncSetAttribute(sim_kernel(t.L.nu, P), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin);
     // check the largest footprints fit
     const size_t sb = mpc_builder_smem_doubles(t.L.nu * t.L.mmax, t.L.nst) * sizeof(double);
-    const size_t ss = mpc_sim_smem_doubles(t.L, t.L.mmax) * sizeof(double);
+    const size_t ss = sim_smem_doubles(t.L, t.L.nu, sim_pad(t.L.mmax)) * sizeof(double);
     if (sb > h->smem_optin || ss > h->smem_optin) {
         g_create_error = "problem too large for shared memory (builder " + std::to_string(sb) + " B, sim " +
                          std::to_string(ss) + " B)";
@@ -289,7 +301,7 @@ extern "C" void mpcgpu_destroy(mpcgpu_handle *h) {
     h->dN.release(); h->dNu.release(); h->dOrder.release(); h->dInvalid.release(); h->dBStatus.release();
     h->dStatus.release(); h->dOffM.release(); h->dOffW.release(); h->dDelta.release(); h->dLambda.release();
     h->dM.release(); h->dW.release(); h->dCost.release(); h->dPart.release(); h->dY.release(); h->dU.release();
-    h->dYs.release(); h->dUopt.release(); h->dCounters.release();
+    h->dYs.release(); h->dUopt.release(); h->dCounters.release(); h->dScratch.release();
     h->pinD.release(); h->pinOut.release(); h->pinI.release();
     for (int i = 0; i < NSTREAM; ++i) {
         if (h->pool[i]) cudaStreamDestroy(h->pool[i]);
@@ -322,25 +334,30 @@ extern "C" int mpcgpu_upload(mpcgpu_handle *h, int n, const int32_t *N, const in
     h->hN.assign(N, N + n); h->hNu.assign(Nu, Nu + n);
     h->hInvalid.assign(n, 0);
     h->hOffM.assign(n, 0); h->hOffW.assign(n, 0);
-    // bucket by m, largest first; illegal horizons never reach a kernel
-    std::vector<std::vector<int>> by_m(L.mmax + 1);
+    // bucket by padded horizon P (4/8/16), largest first; illegal horizons never reach a kernel
+    std::vector<std::vector<int>> by_p(3);
+    int mmax_p[3] = {0, 0, 0};
     long long offM = 0, offW = 0;
     h->n_valid = 0;
     for (int c = 0; c < n; ++c) {
         const int p = N[c], m = Nu[c];
         if (p < 2 || p > L.pmax || m < 1 || m > L.mmax || m >= p) { h->hInvalid[c] = 1; continue; }
-        by_m[m].push_back(c);
-        const long long nz = (long long)nu * m;
-        h->hOffM[c] = offM; offM += (long long)L.nst * nz;
-        h->hOffW[c] = offW; offW += nz * nz;
+        const int P = sim_pad(m), b = P == 4 ? 0 : (P == 8 ? 1 : 2);
+        by_p[b].push_back(c);
+        if (m > mmax_p[b]) mmax_p[b] = m;
+        const long long R = (long long)nu * P;
+        h->hOffM[c] = offM; offM += (long long)L.nst * R;
+        h->hOffW[c] = offW; offW += R * R;
         h->n_valid++;
     }
     h->hOrder.clear(); h->buckets.clear();
-    for (int m = L.mmax; m >= 1; --m) {
-        if (by_m[m].empty()) continue;
-        mpcgpu_handle::Bucket b{m, (int)h->hOrder.size(), (int)by_m[m].size()};
-        h->hOrder.insert(h->hOrder.end(), by_m[m].begin(), by_m[m].end());
-        h->buckets.push_back(b);
+    for (int b = 2; b >= 0; --b) {
+        if (by_p[b].empty()) continue;
+        // heavier candidates first: larger m, then smaller move-suppression weights (more constraint activity)
+        std::stable_sort(by_p[b].begin(), by_p[b].end(), [&](int x, int y) { return Nu[x] > Nu[y]; });
+        mpcgpu_handle::Bucket bk{4 << b, mmax_p[b], (int)h->hOrder.size(), (int)by_p[b].size()};
+        h->hOrder.insert(h->hOrder.end(), by_p[b].begin(), by_p[b].end());
+        h->buckets.push_back(bk);
     }
     const size_t nn = (size_t)(n > 0 ? n : 1);
     CK(h->dN.ensure(nn)); CK(h->dNu.ensure(nn)); CK(h->dOrder.ensure(nn)); CK(h->dInvalid.ensure(nn));
@@ -394,7 +411,16 @@ extern "C" int mpcgpu_run(mpcgpu_handle *h, int cost_mode, int want_traj, void *
         CK(h->dY.ensure(nn * ny * nit)); CK(h->dYs.ensure(nn * ny * nit));
         CK(h->dU.ensure(nn * nu * nit)); CK(h->dUopt.ensure(nn * nu * nit));
     }
-    DevCand C{h->dN.p, h->dNu.p, h->dDelta.p, h->dLambda.p, h->dOffM.p, h->dOffW.p, h->dM.p, h->dW.p, h->dBStatus.p};
+    // spill area: only rows beyond QC (= 16 active constraints) of the P = 16 bucket ever touch it
+    long long scr_stride = 0, scr_items = 0;
+    for (const auto &bk : h->buckets) {
+        const long long sd = (long long)sim_scratch_doubles(nu * bk.P);
+        if (sd > scr_stride) scr_stride = sd;
+        scr_items += (long long)bk.count * runs;
+    }
+    if (scr_stride > 0) CK(h->dScratch.ensure((size_t)(scr_stride * scr_items + 1)));
+    DevCand C{h->dN.p, h->dNu.p, h->dDelta.p, h->dLambda.p, h->dOffM.p, h->dOffW.p, h->dM.p, h->dW.p, h->dBStatus.p,
+              scr_stride > 0 ? h->dScratch.p : nullptr, scr_stride};
     DevOut O{h->dCost.p, h->dPart.p, h->dStatus.p, h->dCounters.p,
              want_traj ? h->dY.p : nullptr, want_traj ? h->dU.p : nullptr, want_traj ? h->dYs.p : nullptr,
              want_traj ? h->dUopt.p : nullptr};
@@ -416,7 +442,7 @@ extern "C" int mpcgpu_run(mpcgpu_handle *h, int cost_mode, int want_traj, void *
     for (int i = 0; i < nfork; ++i) CK(cudaStreamWaitEvent(h->pool[i], h->ev_fork, 0));
     for (int b = 0; b < nb; ++b) {
         const auto &bk = h->buckets[b];
-        const size_t smem = mpc_builder_smem_doubles(nu * bk.m, L.nst) * sizeof(double);
+        const size_t smem = mpc_builder_smem_doubles(nu * bk.mmax, L.nst) * sizeof(double);
         k_build<<<bk.count, BUILD_THREADS, smem, h->pool[b % NSTREAM]>>>(L, T, h->dOrder.p + bk.off, bk.count, C);
         launches++;
     }
@@ -428,17 +454,14 @@ extern "C" int mpcgpu_run(mpcgpu_handle *h, int cost_mode, int want_traj, void *
     // ---- phase 2: closed loops ----
     CK(cudaEventRecord(h->ev_fork, s));
     for (int i = 0; i < nfork; ++i) CK(cudaStreamWaitEvent(h->pool[i], h->ev_fork, 0));
+    long long item0 = 0;
     for (int b = 0; b < nb; ++b) {
         const auto &bk = h->buckets[b];
-        const size_t smem = mpc_sim_smem_doubles(L, bk.m) * sizeof(double);
+        const size_t smem = sim_smem_doubles(L, nu, bk.P) * sizeof(double);
         const int grid = bk.count * runs;
-        cudaStream_t ps = h->pool[b % NSTREAM];
-        switch (nu) {
-            case 1: k_sim<1><<<grid, 32, smem, ps>>>(L, T, h->dOrder.p + bk.off, bk.count, runs, cost_mode, square, C, O); break;
-            case 2: k_sim<2><<<grid, 32, smem, ps>>>(L, T, h->dOrder.p + bk.off, bk.count, runs, cost_mode, square, C, O); break;
-            case 3: k_sim<3><<<grid, 32, smem, ps>>>(L, T, h->dOrder.p + bk.off, bk.count, runs, cost_mode, square, C, O); break;
-            default: k_sim<4><<<grid, 32, smem, ps>>>(L, T, h->dOrder.p + bk.off, bk.count, runs, cost_mode, square, C, O); break;
-        }
+        sim_kernel(nu, bk.P)<<<grid, 32, smem, h->pool[b % NSTREAM]>>>(L, T, h->dOrder.p + bk.off, bk.count, runs, cost_mode,
+                                                                       square, item0, C, O);
+        item0 += grid;
         launches++;
     }
     for (int i = 0; i < nfork; ++i) {

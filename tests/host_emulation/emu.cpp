@@ -1,7 +1,11 @@
-// emu.cpp -- TEST-ONLY host build of the device algorithm (csrc/mpc_core.cuh with MPC_HOST_EMULATION).
-// Lets the not-gpu test-suite exercise the exact kernel source (lane loops serialised) against the
-// oracle.  It is never part of libmpcgpu.so and the product never loads it.
+// emu.cpp -- TEST-ONLY host build of the device algorithm sources:
+//   csrc/mpc_core.cuh (builder, thread-serialised via MPC_HOST_EMULATION) and
+//   csrc/mpc_sim.cuh  (closed-loop warp kernel, executed thread-per-lane through simt.h).
+// Lets the not-gpu test-suite exercise the exact kernel source against the oracle.  It is never part of
+// libmpcgpu.so and the product never loads it.
 #define MPC_HOST_EMULATION 1
+#include "simt.h"
+
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -9,16 +13,40 @@
 #include <vector>
 
 #include "../../model-predictive-control-tuning_b200/csrc/mpc_core.cuh"
+#include "../../model-predictive-control-tuning_b200/csrc/mpc_sim.cuh"
 #include "../../model-predictive-control-tuning_b200/csrc/mpc_tables.h"
 
-template <typename... A>
-static int sim_dispatch(int nu, A &&...a) {
-    switch (nu) {
-        case 1: return mpc_sim_run<1>(a...);
-        case 2: return mpc_sim_run<2>(a...);
-        case 3: return mpc_sim_run<3>(a...);
-        default: return mpc_sim_run<4>(a...);
+template <int NU>
+static int sim_p(int P, const MpcLayout &L, const MpcTables &T, int m, const double *Mg, const double *Wg, int mode, int sel,
+                 double *smem, double *gscr, const MpcRunOut &out) {
+    switch (P) {
+        case 4: return sim_run<NU, 4>(L, T, m, Mg, Wg, mode, sel, smem, gscr, out);
+        case 8: return sim_run<NU, 8>(L, T, m, Mg, Wg, mode, sel, smem, gscr, out);
+        default: return sim_run<NU, 16>(L, T, m, Mg, Wg, mode, sel, smem, gscr, out);
     }
+}
+static int sim_dispatch(int nu, int P, const MpcLayout &L, const MpcTables &T, int m, const double *Mg, const double *Wg,
+                        int mode, int sel, double *smem, double *gscr, const MpcRunOut &out) {
+    switch (nu) {
+        case 1: return sim_p<1>(P, L, T, m, Mg, Wg, mode, sel, smem, gscr, out);
+        case 2: return sim_p<2>(P, L, T, m, Mg, Wg, mode, sel, smem, gscr, out);
+        case 3: return sim_p<3>(P, L, T, m, Mg, Wg, mode, sel, smem, gscr, out);
+        default: return sim_p<4>(P, L, T, m, Mg, Wg, mode, sel, smem, gscr, out);
+    }
+}
+
+// one warp = 32 host threads
+static int run_warp(int nu, int P, const MpcLayout &L, const MpcTables &T, int m, const double *Mg, const double *Wg, int mode,
+                    int sel, const MpcRunOut &out) {
+    std::vector<double> smem(sim_smem_doubles(L, nu, P) + 8, std::nan(""));   // NaN-poison: catches reads of unwritten shared memory
+    std::vector<double> gscr(sim_scratch_doubles(nu * P) + 8, std::nan(""));
+    int status[32];
+    simt_run_warp([&]() {
+        status[threadIdx.x] = sim_dispatch(nu, P, L, T, m, Mg, Wg, mode, sel, smem.data(), gscr.data(), out);
+    });
+    for (int l = 1; l < 32; ++l)
+        if (status[l] != status[0]) return 99;  // non-uniform control flow
+    return status[0];
 }
 
 extern "C" int emu_eval_batch(const mpcgpu_problem *pb, int n, const int *N, const int *Nu, const double *delta,
@@ -33,13 +61,18 @@ extern "C" int emu_eval_batch(const mpcgpu_problem *pb, int n, const int *N, con
     const bool square = ny == nu;
     for (int c = 0; c < n; ++c) {
         const int p = N[c], m = Nu[c], nz = nu * m;
-        if (p < 2 || p > L.pmax || m < 1 || m > L.mmax || m >= p) { if (status) status[c] = 4; continue; }
+        if (p < 2 || p > L.pmax || m < 1 || m > L.mmax || m >= p) {
+            if (status) status[c] = 4;
+            if (cost && mode == 1) for (int i = 0; i < ny; ++i) cost[(size_t)c * ny + i] = NAN;
+            if (cost && mode == 2) cost[c] = NAN;
+            continue;
+        }
+        const int P = sim_pad(m), R = nu * P;
         std::vector<double> bsm(mpc_builder_smem_doubles(nz, L.nst));
-        std::vector<double> Mg((size_t)L.nst * nz), Wg((size_t)nz * nz);
+        std::vector<double> Mg((size_t)L.nst * R), Wg((size_t)R * R);
         int flag = 0;
         int st = mpc_build_candidate(L, T, p, m, delta + (size_t)c * ny, lambda + (size_t)c * nu, bsm.data(), Mg.data(),
                                      Wg.data(), &flag);
-        std::vector<double> ssm(mpc_sim_smem_doubles(L, m) + 8);
         double part[MPC_MAXY + 1];
         if (st == 0) {
             if (mode == 2) {
@@ -49,7 +82,7 @@ extern "C" int emu_eval_batch(const mpcgpu_problem *pb, int n, const int *N, con
                     MpcRunOut out{part, y ? y + (size_t)c * ny * nit : nullptr, u ? u + (size_t)c * nu * nit : nullptr,
                                   ys ? ys + (size_t)c * ny * nit : nullptr, uopt ? uopt + (size_t)c * nu * nit : nullptr,
                                   counters};
-                    int s2 = sim_dispatch(nu, L, T, p, m, Mg.data(), Wg.data(), 2, square ? rn : -1, ssm.data(), out);
+                    int s2 = run_warp(nu, P, L, T, m, Mg.data(), Wg.data(), 2, square ? rn : -1, out);
                     if (s2) st = s2;
                     F += part[0];
                 }
@@ -58,7 +91,7 @@ extern "C" int emu_eval_batch(const mpcgpu_problem *pb, int n, const int *N, con
                 MpcRunOut out{mode == 1 ? cost + (size_t)c * ny : nullptr, y ? y + (size_t)c * ny * nit : nullptr,
                               u ? u + (size_t)c * nu * nit : nullptr, ys ? ys + (size_t)c * ny * nit : nullptr,
                               uopt ? uopt + (size_t)c * nu * nit : nullptr, counters};
-                st = sim_dispatch(nu, L, T, p, m, Mg.data(), Wg.data(), mode, -2, ssm.data(), out);
+                st = run_warp(nu, P, L, T, m, Mg.data(), Wg.data(), mode, -2, out);
             }
         } else if (cost) {
             if (mode == 1) for (int i = 0; i < ny; ++i) cost[(size_t)c * ny + i] = NAN;

@@ -1,0 +1,90 @@
+// simt.h -- TEST-ONLY thread-per-lane emulation of the handful of CUDA warp intrinsics the closed-loop
+// kernel uses, so that csrc/mpc_sim.cuh (the exact kernel source) can be executed on a CPU by the
+// not-gpu test-suite: one std::thread per lane, a std::barrier per warp, shuffles through a shared slot
+// array.  Slow (a barrier per intrinsic) but faithful: per-lane registers, divergence-free control flow
+// and every __syncwarp()/shuffle of the real kernel are exercised.  Never part of the product.
+#pragma once
+#include <barrier>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <functional>
+#include <thread>
+#include <vector>
+
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __restrict__
+#define MPC_SIMT_EMULATION 1
+
+struct SimtDim3 { unsigned x = 0, y = 0, z = 0; };
+struct SimtWarp {
+    std::barrier<> bar{32};
+    double xd[32];
+    long long xi[32];
+    unsigned vote[32];
+};
+static thread_local SimtDim3 threadIdx, blockIdx;
+static thread_local SimtWarp *simt_warp = nullptr;
+
+static inline void __syncwarp(unsigned = 0xffffffffu) { simt_warp->bar.arrive_and_wait(); }
+
+template <typename T>
+static inline T simt_xchg(T v, int src) {
+    static_assert(sizeof(T) <= 8, "");
+    long long raw = 0;
+    std::memcpy(&raw, &v, sizeof(T));
+    simt_warp->xi[threadIdx.x & 31] = raw;
+    simt_warp->bar.arrive_and_wait();
+    long long got = simt_warp->xi[src & 31];
+    simt_warp->bar.arrive_and_wait();
+    T out;
+    std::memcpy(&out, &got, sizeof(T));
+    return out;
+}
+template <typename T>
+static inline T __shfl_sync(unsigned, T v, int src, int width = 32) {
+    const int lane = threadIdx.x & 31;
+    const int base = lane & ~(width - 1);
+    return simt_xchg(v, base + (src & (width - 1)));
+}
+template <typename T>
+static inline T __shfl_xor_sync(unsigned, T v, int mask, int width = 32) {
+    const int lane = threadIdx.x & 31;
+    (void)width;
+    return simt_xchg(v, lane ^ mask);
+}
+template <typename T>
+static inline T __shfl_up_sync(unsigned, T v, unsigned delta, int width = 32) {
+    const int lane = threadIdx.x & 31;
+    const int pos = lane & (width - 1);
+    const int src = (pos >= (int)delta) ? lane - (int)delta : lane;  // CUDA: out-of-segment lanes keep their own value
+    return simt_xchg(v, src);
+}
+static inline int __any_sync(unsigned, int pred) {
+    simt_warp->vote[threadIdx.x & 31] = pred ? 1u : 0u;
+    simt_warp->bar.arrive_and_wait();
+    int r = 0;
+    for (int i = 0; i < 32; ++i) r |= (int)simt_warp->vote[i];
+    simt_warp->bar.arrive_and_wait();
+    return r;
+}
+static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) {
+    return __atomic_fetch_add(p, v, __ATOMIC_RELAXED);
+}
+static inline double __ldg(const double *p) { return *p; }
+
+// run fn() as one warp of 32 lanes
+static inline void simt_run_warp(const std::function<void()> &fn, unsigned block = 0) {
+    SimtWarp w;
+    std::vector<std::thread> th;
+    for (unsigned l = 0; l < 32; ++l)
+        th.emplace_back([&, l]() {
+            threadIdx.x = l;
+            blockIdx.x = block;
+            simt_warp = &w;
+            fn();
+        });
+    for (auto &t : th) t.join();
+}
