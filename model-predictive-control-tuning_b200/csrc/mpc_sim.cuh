@@ -33,6 +33,8 @@ struct MpcRunOut {
     double *cost;                  // GAM: ny slots; VNS: 1 slot (partial sum of this run); RAW: nullptr
     double *y, *u, *ys, *uopt;     // trajectories of this candidate (signals x nit) or nullptr
     unsigned long long *counters;  // [0] constrained QPs, [1] active-set iterations
+    unsigned long long *diag;      // optional per-run {constrained QPs, iterations, max active set, clock cycles}
+    int *trace;                    // optional per-sample {active-set iterations, final active-set size} (debug)
 };
 
 static MPC_HD int sim_pad(int m) { return m <= 4 ? 4 : (m <= 8 ? 8 : 16); }
@@ -119,6 +121,7 @@ struct SimWarp {
     double u[NU];   // uniform: MV levels u(k-1)
     int q;          // uniform: carried active-set size
     unsigned long long n_con, n_it;
+    int qmax;
 
     __device__ __forceinline__ SimWarp(const MpcLayout &L_) : L(L_) {}
 
@@ -273,19 +276,56 @@ struct SimWarp {
         __syncwarp();
         const int qn = sm.misc[0], first = sm.misc[1];
         __syncwarp();
-        for (int a = first; a < qn; ++a) {
+        q = first;
+        rebuild(first, qn);
+    }
+    // Re-append the constraints stored at list positions [from, upto) behind the first `q` (= from on
+    // entry) factor rows, skipping any that has become linearly dependent.  Leaves q = new size.
+    __device__ __forceinline__ void rebuild(int from, int upto) {
+        for (int a = from; a < upto; ++a) {
             const int cid = sm.act[a];
             const double mua = sm.mu[a];
+            __syncwarp();
             double wv[NSLOT];
             w_times_normal(cid, wv, sm.w2);
             const double gam = ndot(cid, sm.w2);
-            const double l2 = schur_vectors(a, sm.w2);
-            double rho = gam - l2;
-            if (!(rho > 0.0)) rho = SIM_DEP_TOL * gam;
-            add_V(a, sm.l, -1.0, wv);
-            commit(cid, a, rho, mua, wv);
+            const double l2 = schur_vectors(q, sm.w2);
+            const double rho = gam - l2;
+            if (rho > SIM_DEP_TOL * gam) {
+                add_V(q, sm.l, -1.0, wv);
+                commit(cid, q, rho, mua, wv);
+                q += 1;
+            } else {
+#pragma unroll
+                for (int s = 0; s < NSLOT; ++s)
+                    if (row[s] == (cid >> 2)) amask[s] &= ~(1 << (cid & 3));
+            }
         }
-        q = qn;
+    }
+    // Receding horizon: the plan computed at k-1 is one sample older at k, so the carried constraint on
+    // (j, c) becomes the guess (j, c-1); those on c == 0 have been applied and leave the set.
+    __device__ __forceinline__ void shift_active_set() {
+        if (lane == 0) {
+            int qn = 0;
+            for (int a = 0; a < q; ++a) {
+                const int cid = sm.act[a], r = cid >> 2;
+                if ((r & (P - 1)) > 0) { sm.act[qn] = (cid & 3) | ((r - 1) << 2); sm.mu[qn] = sm.mu[a]; ++qn; }
+            }
+            sm.misc[0] = qn;
+        }
+        __syncwarp();
+        const int qn = sm.misc[0];
+#pragma unroll
+        for (int s = 0; s < NSLOT; ++s) amask[s] = 0;
+        for (int a = 0; a < qn; ++a) {
+            const int cid = sm.act[a];
+#pragma unroll
+            for (int s = 0; s < NSLOT; ++s)
+                if (row[s] == (cid >> 2)) amask[s] |= (1 << (cid & 3));
+        }
+        __syncwarp();
+        q = 0;
+        rebuild(0, qn);
     }
 
     // Dual active-set QP, warm-started from the carried set.  z (registers) in: z_unc, out: optimum.
@@ -293,6 +333,43 @@ struct SimWarp {
         int it = 0;
         const int itmax = 20 * (NU * m + 10);
         double lv[NSLOT];
+        // ---- which guess?  The carried set as it is (right when the saturation pattern is stationary) or
+        // shifted by one sample (right while a ramp / transient plays out along the horizon).  The carried
+        // factor makes the first guess cheap to score: solve for its multipliers, count the negative ones and,
+        // if there are none, the constraints its solution violates.  Only a bad score pays for the rebuild.
+        if (q > 0) {
+            levels(lv);
+            publish(lv);
+            for (int a = lane; a < q; a += 32) sm.g[a] = -slack_of(sm.act[a]);
+            __syncwarp();
+            schur_solve(q, sm.mu);
+            double mumax = 0.0;
+            for (int a = lane; a < q; a += 32) mumax = fmax(mumax, fabs(sm.mu[a]));
+            mumax = sim_wmax(mumax);
+            int bad = 0;
+            for (int a0 = 0; a0 < q; a0 += 32) {
+                const int a = a0 + lane;
+                bad += __popc(__ballot_sync(SIM_FULL, a < q && sm.mu[a] < -1e-12 * mumax));
+            }
+            if (bad == 0) {
+                double zt[NSLOT];
+#pragma unroll
+                for (int s = 0; s < NSLOT; ++s) zt[s] = z[s];
+                add_V(q, sm.l, 1.0, z);
+                levels(lv);
+#pragma unroll
+                for (int s = 0; s < NSLOT; ++s) {
+                    const double sl[4] = {z[s] - dlo[s], dhi[s] - z[s], lv[s] - ulo[s], uhi[s] - lv[s]};
+#pragma unroll
+                    for (int type = 0; type < 4; ++type)
+                        bad += __popc(__ballot_sync(SIM_FULL, valid[s] && !(amask[s] & (1 << type)) && sl[type] < -SIM_VIOL_TOL));
+                }
+#pragma unroll
+                for (int s = 0; s < NSLOT; ++s) z[s] = zt[s];
+            }
+            __syncwarp();
+            if (bad > 1) { it += 1; shift_active_set(); }
+        }
         // ---- warm start on the carried set: mu = S^-1 (b_A - N_A' z_unc), shed negative multipliers ----
         while (q > 0) {
             levels(lv);
@@ -336,6 +413,17 @@ struct SimWarp {
                     if (sl[type] < bv || (sl[type] == bv && bi >= 0 && id < bi)) { bv = sl[type]; bi = id; }
                 }
             }
+#ifndef SIM_PIVOT_MOST_VIOLATED
+            {   // pivot rule: among the violated constraints take the EARLIEST horizon index first (then the
+                // most violated).  Any violated constraint is a valid Goldfarb-Idnani pivot; walking the
+                // horizon in time order follows how rate/level saturation propagates and avoids most of the
+                // add/drop churn of the most-violated rule (measured: 233 -> see DESIGN.md).
+                double ckey = bi >= 0 ? (double)(row[0] & (P - 1)) : 1e9;
+                int dummy = bi >= 0 ? 0 : -1;
+                sim_wargmin(ckey, dummy);
+                if (bi >= 0 && (double)(row[0] & (P - 1)) != ckey) { bv = -SIM_VIOL_TOL; bi = -1; }
+            }
+#endif
             sim_wargmin(bv, bi);
             if (bi < 0) break;
             const int p = bi;
@@ -409,6 +497,7 @@ struct SimWarp {
             }
         }
         n_it += it;
+        if (q > qmax) qmax = q;
         return 0;
     }
 
@@ -494,7 +583,7 @@ __device__ __forceinline__ int sim_run(const MpcLayout &L, const MpcTables &T, i
         sm.chd = ip; ip += nch; sm.chj = ip; ip += nch; sm.role = ip; ip += nst;
         sm.act = ip; ip += R; sm.dflag = ip; ip += R; sm.misc = ip;
     }
-    wp.gscr = gscr; wp.W = Wg; wp.lane = lane; wp.m = m; wp.q = 0; wp.n_con = 0; wp.n_it = 0;
+    wp.gscr = gscr; wp.W = Wg; wp.lane = lane; wp.m = m; wp.q = 0; wp.n_con = 0; wp.n_it = 0; wp.qmax = 0;
 #pragma unroll
     for (int s = 0; s < NSLOT; ++s) {
         const int r = s * 32 + lane;
@@ -618,12 +707,17 @@ __device__ __forceinline__ int sim_run(const MpcLayout &L, const MpcTables &T, i
         build_st(sm.sig, nit - 1, false);
         const int rc = wp.controller_move();
         if (rc) status = rc;
-        // uopt levels: inclusive scan of z (u(-1) = 0)
-        double lv[NSLOT];
-        wp.levels(lv);
+        // Uopt rows = SEQUENTIAL cumulative sum of the moves from u(-1) = 0: a move that is exactly 0 must
+        // repeat the previous level bit-for-bit, because VNS2.m:183-191 divides by these differences
+        // (a tree-ordered scan would turn exact zeros into 1-ulp noise and Jnu terms of 1e+30).
 #pragma unroll
         for (int s = 0; s < NSLOT; ++s)
-            if (wp.row[s] < R) sm.uopt[wp.row[s]] = lv[s];   // [j*P + c]
+            if (wp.row[s] < R) sm.z[wp.row[s]] = wp.z[s];
+        __syncwarp();
+        for (int j = lane; j < NU; j += 32) {
+            double lvl = 0.0;
+            for (int c = 0; c < P; ++c) { lvl += sm.z[j * P + c]; sm.uopt[j * P + c] = lvl; }
+        }
         __syncwarp();
         if (mode == 2) {  // Jnu (VNS2.m:183-191)
             double part = 0.0;
@@ -650,8 +744,10 @@ __device__ __forceinline__ int sim_run(const MpcLayout &L, const MpcTables &T, i
         if ((k & (SIM_CH - 1)) == 0) stage_signals(k);
         const double *sigrow = sm.sig + (size_t)(k & (SIM_CH - 1)) * nsig;
         build_st(sigrow, k, true);
+        const unsigned long long it_before = wp.n_it;
         const int rc = wp.controller_move();
         if (rc) status = rc;
+        if (out.trace && lane == 0) { out.trace[2 * k] = (int)(wp.n_it - it_before); out.trace[2 * k + 1] = wp.q; }
         // apply the first move of every input
 #pragma unroll
         for (int j = 0; j < NU; ++j) {
@@ -713,5 +809,6 @@ __device__ __forceinline__ int sim_run(const MpcLayout &L, const MpcTables &T, i
         atomicAdd(out.counters + 0, wp.n_con);
         atomicAdd(out.counters + 1, wp.n_it);
     }
+    if (out.diag && lane == 0) { out.diag[0] = wp.n_con; out.diag[1] = wp.n_it; out.diag[2] = (unsigned long long)wp.qmax; }
     return status;
 }

@@ -52,6 +52,7 @@ struct DevOut {
     int *status;    // n
     unsigned long long *counters;  // [0] constrained QPs [1] active-set iterations
     double *y, *u, *ys, *uopt;     // optional trajectories
+    unsigned long long *diag;      // optional per-run diagnostics (4 per run)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -94,10 +95,14 @@ __global__ void __launch_bounds__(32) k_sim(const MpcLayout L, const MpcTables T
     out.ys = O.ys ? O.ys + (size_t)c * ny * nit : nullptr;
     out.uopt = O.uopt ? O.uopt + (size_t)c * NU * nit : nullptr;
     out.counters = O.counters;
+    out.diag = O.diag ? O.diag + 4 * ((size_t)c * runs + run) : nullptr;
+    out.trace = nullptr;
+    const long long t_start = clock64();
     const int sel = mode == 2 ? (square ? run : -1) : -2;
     double *gscr = C.scratch ? C.scratch + (size_t)(item0 + item) * C.scratch_stride : nullptr;
     const int st = sim_run<NU, P>(L, T, m, C.M + C.offM[c], C.W + C.offW[c], mode, sel, smem_s, gscr, out);
     if (st != 0 && (threadIdx.x & 31) == 0) atomicMax(O.status + c, st);
+    if (out.diag && (threadIdx.x & 31) == 0) out.diag[3] = (unsigned long long)(clock64() - t_start);
 }
 
 typedef void (*sim_kernel_t)(const MpcLayout, const MpcTables, const int *, int, int, int, int, long long, DevCand, DevOut);
@@ -190,7 +195,9 @@ struct mpcgpu_handle {
     DBuf<int> dN, dNu, dOrder, dInvalid, dBStatus, dStatus;
     DBuf<long long> dOffM, dOffW;
     DBuf<double> dDelta, dLambda, dM, dW, dCost, dPart, dY, dU, dYs, dUopt, dScratch;
-    DBuf<unsigned long long> dCounters;
+    DBuf<unsigned long long> dCounters, dDiag;
+    bool want_diag = false;
+    int last_runs = 1;
     HBuf<double> pinD, pinOut;
     HBuf<int> pinI;
     mpcgpu_counters cnt = {};
@@ -301,7 +308,7 @@ extern "C" void mpcgpu_destroy(mpcgpu_handle *h) {
     h->dN.release(); h->dNu.release(); h->dOrder.release(); h->dInvalid.release(); h->dBStatus.release();
     h->dStatus.release(); h->dOffM.release(); h->dOffW.release(); h->dDelta.release(); h->dLambda.release();
     h->dM.release(); h->dW.release(); h->dCost.release(); h->dPart.release(); h->dY.release(); h->dU.release();
-    h->dYs.release(); h->dUopt.release(); h->dCounters.release(); h->dScratch.release();
+    h->dYs.release(); h->dUopt.release(); h->dCounters.release(); h->dScratch.release(); h->dDiag.release();
     h->pinD.release(); h->pinOut.release(); h->pinI.release();
     for (int i = 0; i < NSTREAM; ++i) {
         if (h->pool[i]) cudaStreamDestroy(h->pool[i]);
@@ -423,7 +430,13 @@ extern "C" int mpcgpu_run(mpcgpu_handle *h, int cost_mode, int want_traj, void *
               scr_stride > 0 ? h->dScratch.p : nullptr, scr_stride};
     DevOut O{h->dCost.p, h->dPart.p, h->dStatus.p, h->dCounters.p,
              want_traj ? h->dY.p : nullptr, want_traj ? h->dU.p : nullptr, want_traj ? h->dYs.p : nullptr,
-             want_traj ? h->dUopt.p : nullptr};
+             want_traj ? h->dUopt.p : nullptr, nullptr};
+    if (h->want_diag) {
+        CK(h->dDiag.ensure(4 * nn * runs));
+        CK(cudaMemsetAsync(h->dDiag.p, 0, sizeof(unsigned long long) * 4 * nn * runs, s));
+        O.diag = h->dDiag.p;
+    }
+    h->last_runs = runs;
     const MpcTables T = dev_tables(h);
     CK(cudaEventRecord(h->ev_t0, s));
     CK(cudaMemsetAsync(h->dStatus.p, 0, sizeof(int) * nn, s));
@@ -577,4 +590,15 @@ extern "C" int mpcgpu_measure_fp64_peak(int device, double *tflops) {
     cudaFree(d);
     *tflops = best;
     return MPCGPU_OK;
+}
+
+// Internal diagnostics (not part of the public ABI): per-run {constrained QPs, active-set iterations,
+// largest active set, SM clock cycles} of the last run; enable before mpcgpu_run.
+extern "C" int mpcgpu_debug_enable_diag(mpcgpu_handle *h, int on) { if (!h) return 1; h->want_diag = on != 0; return 0; }
+extern "C" int mpcgpu_debug_get_diag(mpcgpu_handle *h, unsigned long long *out) {
+    if (!h || !out || !h->ran || !h->dDiag.p) return 1;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(out, h->dDiag.p, sizeof(unsigned long long) * 4 * (size_t)h->n * h->last_runs, cudaMemcpyDeviceToHost));
+    return 0;
 }

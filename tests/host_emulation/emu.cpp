@@ -49,6 +49,9 @@ static int run_warp(int nu, int P, const MpcLayout &L, const MpcTables &T, int m
     return status[0];
 }
 
+static int *g_trace = nullptr;
+extern "C" void emu_set_trace(int *p) { g_trace = p; }
+
 extern "C" int emu_eval_batch(const mpcgpu_problem *pb, int n, const int *N, const int *Nu, const double *delta,
                               const double *lambda, int mode, double *cost, double *y, double *u, double *ys,
                               double *uopt, int *status, unsigned long long *counters, char *err, int errlen) {
@@ -81,7 +84,7 @@ extern "C" int emu_eval_batch(const mpcgpu_problem *pb, int n, const int *N, con
                 for (int rn = 0; rn < runs; ++rn) {
                     MpcRunOut out{part, y ? y + (size_t)c * ny * nit : nullptr, u ? u + (size_t)c * nu * nit : nullptr,
                                   ys ? ys + (size_t)c * ny * nit : nullptr, uopt ? uopt + (size_t)c * nu * nit : nullptr,
-                                  counters};
+                                  counters, nullptr, nullptr};
                     int s2 = run_warp(nu, P, L, T, m, Mg.data(), Wg.data(), 2, square ? rn : -1, out);
                     if (s2) st = s2;
                     F += part[0];
@@ -90,7 +93,7 @@ extern "C" int emu_eval_batch(const mpcgpu_problem *pb, int n, const int *N, con
             } else {
                 MpcRunOut out{mode == 1 ? cost + (size_t)c * ny : nullptr, y ? y + (size_t)c * ny * nit : nullptr,
                               u ? u + (size_t)c * nu * nit : nullptr, ys ? ys + (size_t)c * ny * nit : nullptr,
-                              uopt ? uopt + (size_t)c * nu * nit : nullptr, counters};
+                              uopt ? uopt + (size_t)c * nu * nit : nullptr, counters, nullptr, g_trace};
                 st = run_warp(nu, P, L, T, m, Mg.data(), Wg.data(), mode, -2, out);
             }
         } else if (cost) {

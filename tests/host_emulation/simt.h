@@ -70,6 +70,15 @@ static inline int __any_sync(unsigned, int pred) {
     simt_warp->bar.arrive_and_wait();
     return r;
 }
+static inline unsigned __ballot_sync(unsigned, int pred) {
+    simt_warp->vote[threadIdx.x & 31] = pred ? 1u : 0u;
+    simt_warp->bar.arrive_and_wait();
+    unsigned r = 0;
+    for (int i = 0; i < 32; ++i) r |= simt_warp->vote[i] << i;
+    simt_warp->bar.arrive_and_wait();
+    return r;
+}
+static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) {
     return __atomic_fetch_add(p, v, __ATOMIC_RELAXED);
 }
