@@ -26,7 +26,7 @@
 // ---------------------------------------------------------------------------------------------
 // Builder: one CTA per candidate.
 // Shared memory (doubles): Hs[nz*nz] | B[(nst+nz)*nz]   (B column-major: B[col*nz + row])
-// Outputs (global): Mg[nst*R] = M in deviation coordinates, stored [col][row]; Wg[R*R] = H^-1 (padded).
+// Outputs (global): Mg[nst*R] = M in deviation coordinates, stored [col][row]; Wg[2*R*R] = H^-1 (padded) followed by its running row sums.
 // ---------------------------------------------------------------------------------------------
 static MPC_HD size_t mpc_builder_smem_doubles(int nz, int nst) { return (size_t)nz * nz + (size_t)(nst + nz) * nz; }
 
@@ -143,7 +143,15 @@ MPC_FN int mpc_build_candidate(const MpcLayout &L, const MpcTables &T, int p, in
         TFOR(idx, R * R) {
             const int r1 = idx / R, r2 = idx - r1 * R;
             const int j1 = r1 / P, c1 = r1 - j1 * P, j2 = r2 / P, c2 = r2 - j2 * P;
-            Wg[idx] = (c1 < m && c2 < m) ? B[(size_t)(ns + c1 * nu + j1) * nz + (c2 * nu + j2)] : 0.0;
+            double acc = 0.0, wr = 0.0;   // running sum over the horizon index of row block j1: W * (level normal)
+            if (c2 < m)
+                for (int cc = 0; cc <= c1 && cc < m; ++cc) {
+                    const double v = B[(size_t)(ns + cc * nu + j1) * nz + (c2 * nu + j2)];
+                    acc += v;
+                    if (cc == c1) wr = v;
+                }
+            Wg[idx] = (c1 < m) ? wr : 0.0;
+            Wg[(size_t)R * R + idx] = (c1 < m) ? acc : 0.0;
         }
     }
     TSYNC();

@@ -38,7 +38,7 @@ struct MpcRunOut {
 };
 
 static MPC_HD int sim_pad(int m) { return m <= 4 ? 4 : (m <= 8 ? 8 : 16); }
-static MPC_HD int sim_qc(int R) { return R <= 24 ? R : 16; }
+static MPC_HD int sim_qc(int R) { return R <= 24 ? R : 24; }
 static MPC_HD int sim_hl(const MpcLayout &L) {
     int h = 1;
     for (int j = 0; j < L.nw; ++j) h = L.hlen[j] > h ? L.hlen[j] : h;
@@ -47,7 +47,7 @@ static MPC_HD int sim_hl(const MpcLayout &L) {
 // per-run global scratch (doubles) for V columns / Li rows beyond QC
 static MPC_HD size_t sim_scratch_doubles(int R) {
     const int qc = sim_qc(R);
-    return (size_t)(R - qc) * R + ((size_t)R * (R + 1) / 2 - (size_t)qc * (qc + 1) / 2);
+    return 2 * (size_t)(R - qc) * R;   // V columns and (full-length) Li rows beyond QC
 }
 static MPC_HD size_t sim_smem_doubles(const MpcLayout &L, int nu, int P) {
     const int R = nu * P, qc = sim_qc(R), nch = L.ny * L.nw, HL = sim_hl(L);
@@ -59,15 +59,15 @@ static MPC_HD size_t sim_smem_doubles(const MpcLayout &L, int nu, int P) {
     n += (size_t)SIM_CH * (2 * L.ny + L.nd);  // sig
     n += (size_t)nu * P;                      // uopt
     n += 4 * nu;                              // bnd
-    n += 4 * (size_t)R;                       // z, lvl, w, w2
+    n += 6 * (size_t)R;                       // z, lvl, w, wsc, w2, w2sc
     n += 4 * (size_t)R;                       // g, l, rr, mu
-    n += (size_t)qc * R + (size_t)qc * (qc + 1) / 2;  // V, Li
+    n += (size_t)qc * R + (size_t)qc * qc;    // V, Li (full stride)
     n += (2 * nch + L.nst + 2 * R + 8 + 1) / 2 + 1;   // ints: chd, chj, role, act, dflag, misc
     return n;
 }
 
 struct SimSm {
-    double *M, *st, *x, *xol, *hist, *cha, *chb0, *chb1, *chg, *sig, *uopt, *bnd, *z, *lvl, *w, *w2, *g, *l, *rr, *mu, *V, *Li;
+    double *M, *st, *x, *xol, *hist, *cha, *chb0, *chb1, *chg, *sig, *uopt, *bnd, *z, *lvl, *w, *wsc, *w2, *w2sc, *g, *l, *rr, *mu, *V, *Li;
     int *chd, *chj, *role, *act, *dflag, *misc;
 };
 
@@ -104,8 +104,7 @@ template <int NU, int P>
 struct SimWarp {
     static constexpr int R = NU * P;
     static constexpr int NSLOT = (R + 31) / 32;
-    static constexpr int QC = (R <= 24) ? R : 16;
-    static constexpr int LI_SM = QC * (QC + 1) / 2;
+    static constexpr int QC = (R <= 24) ? R : 24;
 
     const MpcLayout &L;
     SimSm sm;
@@ -126,8 +125,9 @@ struct SimWarp {
     __device__ __forceinline__ SimWarp(const MpcLayout &L_) : L(L_) {}
 
     __device__ __forceinline__ double *Vcol(int a) const { return a < QC ? sm.V + (size_t)a * R : gscr + (size_t)(a - QC) * R; }
+    // row a of the inverse Cholesky factor: entries [0..a]; QC doubles long in shared memory, R in the spill
     __device__ __forceinline__ double *Lirow(int a) const {
-        return a < QC ? sm.Li + (a * (a + 1)) / 2 : gscr + (size_t)(R - QC) * R + ((a * (a + 1)) / 2 - LI_SM);
+        return a < QC ? sm.Li + (size_t)a * QC : gscr + (size_t)(R - QC) * R + (size_t)(a - QC) * R;
     }
 
     // u(k+c) for this lane's rows: u_j(k-1) + inclusive scan of z over c within the input's segment
@@ -161,84 +161,100 @@ struct SimWarp {
             default: return b[3] - sm.lvl[r];
         }
     }
-    // n_cid' x for a published row vector x (shared memory)
-    __device__ __forceinline__ double ndot(int cid, const double *x) const {
+    // n_cid' x where x and its per-input inclusive scan xs have been published (x: rate normals, xs: level)
+    __device__ __forceinline__ double ndot(int cid, const double *x, const double *xs) const {
         const int type = cid & 3, r = cid >> 2;
-        if (type < 2) return type == 0 ? x[r] : -x[r];
-        const int base = r & ~(P - 1), c = r & (P - 1);
-        double acc = 0.0;
-        for (int c2 = 0; c2 <= c; ++c2) acc += x[base + c2];
-        return type == 2 ? acc : -acc;
+        const double v = type < 2 ? x[r] : xs[r];
+        return (type & 1) ? -v : v;
     }
-    // wv = W n_cid for this lane's rows (W symmetric: rows read coalesced); also published to dst
-    __device__ __forceinline__ void w_times_normal(int cid, double (&wv)[NSLOT], double *dst) const {
+    // wv = W n_cid for this lane's rows.  Wg holds 2R rows of R: rows [0,R) are W, rows [R,2R) the running
+    // sums of W's rows over the horizon index inside each input block, i.e. W times a level normal: one
+    // coalesced load per row whatever the constraint.  Publishes wv and its segmented scan to dst / dsts.
+    __device__ __forceinline__ void w_times_normal(int cid, double (&wv)[NSLOT], double *dst, double *dsts) const {
         const int type = cid & 3, r = cid >> 2;
-        const double sg = (type == 0 || type == 2) ? 1.0 : -1.0;
+        const double sg = (type & 1) ? -1.0 : 1.0;
+        const double *src = W + (size_t)(type < 2 ? r : R + r) * R;
+#pragma unroll
+        for (int s = 0; s < NSLOT; ++s) wv[s] = row[s] < R ? sg * src[row[s]] : 0.0;
 #pragma unroll
         for (int s = 0; s < NSLOT; ++s) {
-            double acc = 0.0;
-            if (row[s] < R) {
-                if (type < 2) {
-                    acc = W[(size_t)r * R + row[s]];
-                } else {
-                    const int base = r & ~(P - 1), c = r & (P - 1);
-#pragma unroll 4
-                    for (int c2 = 0; c2 <= c; ++c2) acc += W[(size_t)(base + c2) * R + row[s]];
-                }
-                acc *= sg;
-                dst[row[s]] = acc;
+            double v = wv[s];
+            const int c = row[s] & (P - 1);
+#pragma unroll
+            for (int off = 1; off < P; off <<= 1) {
+                const double t = __shfl_up_sync(SIM_FULL, v, off, P);
+                if (c >= off) v += t;
             }
-            wv[s] = acc;
+            if (row[s] < R) { dst[row[s]] = wv[s]; dsts[row[s]] = v; }
         }
         __syncwarp();
     }
-    // g = N' x (x published), l = Li g, rr = Li' l for the first qq active constraints; returns |l|^2
-    __device__ __forceinline__ double schur_vectors(int qq, const double *x) const {
-        for (int a = lane; a < qq; a += 32) sm.g[a] = ndot(sm.act[a], x);
+    // g = N' x (x, xs published), l = Li g, rr = Li' l for the first qq active constraints; returns |l|^2
+    __device__ __forceinline__ double schur_vectors(int qq, const double *x, const double *xs) const {
+        for (int a = lane; a < qq; a += 32) sm.g[a] = ndot(sm.act[a], x, xs);
         __syncwarp();
+        const double l2 = tri_lower(qq);
+        tri_upper(qq, sm.rr);
+        return l2;
+    }
+    // l = Li g (lane a owns row a); returns |l|^2
+    __device__ __forceinline__ double tri_lower(int qq) const {
         double part = 0.0;
         for (int a = lane; a < qq; a += 32) {
             const double *row_a = Lirow(a);
-            double acc = 0.0;
-            for (int b = 0; b <= a; ++b) acc += row_a[b] * sm.g[b];
+            double a0 = 0.0, a1 = 0.0;
+            int b = 0;
+            for (; b + 1 <= a; b += 2) { a0 = fma(row_a[b], sm.g[b], a0); a1 = fma(row_a[b + 1], sm.g[b + 1], a1); }
+            if (b <= a) a0 = fma(row_a[b], sm.g[b], a0);
+            const double acc = a0 + a1;
             sm.l[a] = acc;
             part += acc * acc;
         }
         const double l2 = sim_wsum(part);
         __syncwarp();
+        return l2;
+    }
+    // out = Li' l (lane a owns column a)
+    __device__ __forceinline__ void tri_upper(int qq, double *out) const {
+        const int qs = qq < QC ? qq : QC;
         for (int a = lane; a < qq; a += 32) {
-            double acc = 0.0;
-            for (int b = a; b < qq; ++b) acc += Lirow(b)[a] * sm.l[b];
-            sm.rr[a] = acc;
+            double a0 = 0.0, a1 = 0.0;
+            int b = a;
+            for (; b + 1 < qs; b += 2) { a0 = fma(sm.Li[(size_t)b * QC + a], sm.l[b], a0); a1 = fma(sm.Li[(size_t)(b + 1) * QC + a], sm.l[b + 1], a1); }
+            if (b < qs) { a0 = fma(sm.Li[(size_t)b * QC + a], sm.l[b], a0); ++b; }
+            if (b < QC) b = QC;
+            for (; b < qq; ++b) a0 = fma(Lirow(b)[a], sm.l[b], a0);   // spilled rows (rare)
+            out[a] = a0 + a1;
         }
         __syncwarp();
-        return l2;
     }
     // l = Li g, mu_out = Li' l  (g already in sm.g)
     __device__ __forceinline__ void schur_solve(int qq, double *mu_out) const {
-        for (int a = lane; a < qq; a += 32) {
-            const double *row_a = Lirow(a);
-            double acc = 0.0;
-            for (int b = 0; b <= a; ++b) acc += row_a[b] * sm.g[b];
-            sm.l[a] = acc;
-        }
-        __syncwarp();
-        for (int a = lane; a < qq; a += 32) {
-            double acc = 0.0;
-            for (int b = a; b < qq; ++b) acc += Lirow(b)[a] * sm.l[b];
-            mu_out[a] = acc;
-        }
-        __syncwarp();
+        tri_lower(qq);
+        tri_upper(qq, mu_out);
     }
-    // x_rows -= / += sum_a coef[a] * V_a   (per-lane rows)
+    // x_rows += sign * sum_a coef[a] * V_a   (per-lane rows)
     __device__ __forceinline__ void add_V(int qq, const double *coef, double sign, double (&x)[NSLOT]) const {
-        for (int a = 0; a < qq; ++a) {
-            const double ca = sign * coef[a];
+        const int qs = qq < QC ? qq : QC;
+        double acc[NSLOT];
+#pragma unroll
+        for (int s = 0; s < NSLOT; ++s) acc[s] = 0.0;
+#pragma unroll 4
+        for (int a = 0; a < qs; ++a) {
+            const double ca = coef[a];
+#pragma unroll
+            for (int s = 0; s < NSLOT; ++s)
+                if (row[s] < R) acc[s] = fma(ca, sm.V[(size_t)a * R + row[s]], acc[s]);
+        }
+        for (int a = QC; a < qq; ++a) {   // spilled columns (rare)
+            const double ca = coef[a];
             const double *va = Vcol(a);
 #pragma unroll
             for (int s = 0; s < NSLOT; ++s)
-                if (row[s] < R) x[s] += ca * va[row[s]];
+                if (row[s] < R) acc[s] = fma(ca, va[row[s]], acc[s]);
         }
+#pragma unroll
+        for (int s = 0; s < NSLOT; ++s) x[s] += sign * acc[s];
     }
     // commit constraint cid at position a: V_a = dir / sqrt(rho), Li row a = [-rr'/sqrt(rho), 1/sqrt(rho)]
     __device__ __forceinline__ void commit(int cid, int a, double rho, double mu_new, const double (&dir)[NSLOT]) {
@@ -287,9 +303,9 @@ struct SimWarp {
             const double mua = sm.mu[a];
             __syncwarp();
             double wv[NSLOT];
-            w_times_normal(cid, wv, sm.w2);
-            const double gam = ndot(cid, sm.w2);
-            const double l2 = schur_vectors(q, sm.w2);
+            w_times_normal(cid, wv, sm.w2, sm.w2sc);
+            const double gam = ndot(cid, sm.w2, sm.w2sc);
+            const double l2 = schur_vectors(q, sm.w2, sm.w2sc);
             const double rho = gam - l2;
             if (rho > SIM_DEP_TOL * gam) {
                 add_V(q, sm.l, -1.0, wv);
@@ -429,11 +445,11 @@ struct SimWarp {
             const int p = bi;
             double sp = bv, mu_p = 0.0;
             double wv[NSLOT];
-            w_times_normal(p, wv, sm.w);
-            const double gamma = ndot(p, sm.w);
+            w_times_normal(p, wv, sm.w, sm.wsc);
+            const double gamma = ndot(p, sm.w, sm.wsc);
             for (;;) {
                 if (++it > itmax) { n_it += it; return 2; }
-                const double l2 = schur_vectors(q, sm.w);
+                const double l2 = schur_vectors(q, sm.w, sm.wsc);
                 const double rho = gamma - l2;
                 const int dependent = !(rho > SIM_DEP_TOL * gamma);
                 double t1 = SIM_INF;
@@ -485,13 +501,7 @@ struct SimWarp {
             worst = sim_wmax(worst);
             __syncwarp();
             if (worst > 1e-13) {
-                for (int a = lane; a < q; a += 32) {
-                    const double *row_a = Lirow(a);
-                    double acc = 0.0;
-                    for (int b = 0; b <= a; ++b) acc += row_a[b] * sm.g[b];
-                    sm.l[a] = acc;
-                }
-                __syncwarp();
+                tri_lower(q);
                 add_V(q, sm.l, 1.0, z);
                 __syncwarp();
             }
@@ -549,7 +559,7 @@ struct SimWarp {
 // ------------------------------------------------------------------------------------------------
 // One closed-loop run.  sel: -2 user set-point (GAM / RAW); -1 VNS unit step on every output;
 // i >= 0 VNS unit step on output i only (VNS2.m:148-165).  mode: 0 RAW, 1 GAM, 2 VNS.
-// Mg: nst x R (row-padded, [col][row]); Wg: R x R.
+// Mg: nst x R (row-padded, [col][row]); Wg: 2R x R (W, then W times the level normals).
 // ------------------------------------------------------------------------------------------------
 template <int NU, int P>
 __device__ __forceinline__ int sim_run(const MpcLayout &L, const MpcTables &T, int m, const double *__restrict__ Mg,
@@ -557,7 +567,7 @@ __device__ __forceinline__ int sim_run(const MpcLayout &L, const MpcTables &T, i
                                        const MpcRunOut &out) {
     constexpr int R = NU * P;
     constexpr int NSLOT = (R + 31) / 32;
-    constexpr int QC = (R <= 24) ? R : 16;
+    constexpr int QC = (R <= 24) ? R : 24;
     const int lane = threadIdx.x & 31;
     const int ny = L.ny, nd = L.nd, nw = L.nw, nch = ny * nw, nst = L.nst, nit = L.nit;
     const int HL = sim_hl(L);
@@ -575,10 +585,10 @@ __device__ __forceinline__ int sim_run(const MpcLayout &L, const MpcTables &T, i
         sm.sig = p; p += (size_t)SIM_CH * nsig;
         sm.uopt = p; p += NU * P;
         sm.bnd = p; p += 4 * NU;
-        sm.z = p; p += R; sm.lvl = p; p += R; sm.w = p; p += R; sm.w2 = p; p += R;
+        sm.z = p; p += R; sm.lvl = p; p += R; sm.w = p; p += R; sm.wsc = p; p += R; sm.w2 = p; p += R; sm.w2sc = p; p += R;
         sm.g = p; p += R; sm.l = p; p += R; sm.rr = p; p += R; sm.mu = p; p += R;
         sm.V = p; p += (size_t)QC * R;
-        sm.Li = p; p += (size_t)QC * (QC + 1) / 2;
+        sm.Li = p; p += (size_t)QC * QC;
         int *ip = (int *)p;
         sm.chd = ip; ip += nch; sm.chj = ip; ip += nch; sm.role = ip; ip += nst;
         sm.act = ip; ip += R; sm.dflag = ip; ip += R; sm.misc = ip;

@@ -354,7 +354,7 @@ extern "C" int mpcgpu_upload(mpcgpu_handle *h, int n, const int32_t *N, const in
         if (m > mmax_p[b]) mmax_p[b] = m;
         const long long R = (long long)nu * P;
         h->hOffM[c] = offM; offM += (long long)L.nst * R;
-        h->hOffW[c] = offW; offW += R * R;
+        h->hOffW[c] = offW; offW += 2 * R * R;
         h->n_valid++;
     }
     h->hOrder.clear(); h->buckets.clear();
