@@ -360,8 +360,16 @@ extern "C" int mpcgpu_upload(mpcgpu_handle *h, int n, const int32_t *N, const in
     h->hOrder.clear(); h->buckets.clear();
     for (int b = 2; b >= 0; --b) {
         if (by_p[b].empty()) continue;
-        // heavier candidates first: larger m, then smaller move-suppression weights (more constraint activity)
-        std::stable_sort(by_p[b].begin(), by_p[b].end(), [&](int x, int y) { return Nu[x] > Nu[y]; });
+        // heaviest first, so that the longest closed loops start at t = 0: work grows with the number of
+        // moves and with how hard the controller pushes against the MV limits (large delta / small lambda)
+        std::vector<double> score(n, 0.0);
+        for (int c : by_p[b]) {
+            double dmax = 0.0, lmin = 1e300;
+            for (int i = 0; i < ny; ++i) dmax = std::max(dmax, std::fabs(delta[(size_t)c * ny + i]));
+            for (int j = 0; j < nu; ++j) lmin = std::min(lmin, std::fabs(lambda[(size_t)c * nu + j]));
+            score[c] = std::log10(dmax / (lmin + 1e-300) + 1e-300) + 0.15 * Nu[c];
+        }
+        std::stable_sort(by_p[b].begin(), by_p[b].end(), [&](int x, int y) { return score[x] > score[y]; });
         mpcgpu_handle::Bucket bk{4 << b, mmax_p[b], (int)h->hOrder.size(), (int)by_p[b].size()};
         h->hOrder.insert(h->hOrder.end(), by_p[b].begin(), by_p[b].end());
         h->buckets.push_back(bk);
