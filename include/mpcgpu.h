@@ -127,6 +127,47 @@ int mpcgpu_device_count(void);
  * this path (MEASURED_PEAKS.json has no fp64 entry). */
 int mpcgpu_measure_fp64_peak(int device, double *tflops);
 
+
+/* ------------------------------------------------------------------------------------------------
+ * DTC-GPC batched sweep (BASELINE.json configs[3]): the unconstrained dead-time-compensated GPC of
+ *   /root/reference/DTC-GPC/DTC_GPC_WW.m:56-164  (gain K = (H'QH+W)\H'Q, optimal predictor, control loop)
+ * built from MatG.m:38-74, diophantine.m:15-79, diophantineMIMO.m:14-22, deltaUFree.m:12-63,
+ * BA_MIMO.m:16-72, descompMPC.m:19-43, cell2mat2.m:25-58, OptimalPredictor2.m:24-40.
+ * One candidate = (p[ny], m[nu], delta[ny], lambda[nu], robustness filter Fr per output).  The filter
+ * coefficients are inputs (filter design is outside the hot path).  All channel matrices row-major.
+ * ---------------------------------------------------------------------------------------------- */
+#define MPCGPU_DTC_MAXF 8 /* max filter polynomial length */
+typedef struct {
+    int32_t ny, nu, nq, nit;
+    int32_t pmax, mmax;          /* sweep bounds on the prediction window p_i and control horizon m_j */
+    int32_t k_start;             /* 1-based first sample at which the controller acts (DTC_GPC_WW.m:128: 4) */
+    int32_t reserved;
+    const double *ma, *mb0, *mb1; const int32_t *md;   /* conditioned discrete model Pnz = c2d(L*Pn*R), ny x nu */
+    const double *pa, *pb0, *pb1; const int32_t *pd;   /* discrete process P (unscaled), ny x nu              */
+    const double *qa, *qb0, *qb1; const int32_t *qd;   /* discrete disturbance model Pq (unscaled), ny x nq   */
+    const double *L, *R;                               /* conditioning diagonals, ny and nu                   */
+    const double *r;                                   /* ny x nit reference (unscaled)                       */
+    const double *q;                                   /* nq x nit disturbance                                */
+} mpcgpu_dtc_problem;
+
+typedef struct mpcgpu_dtc_handle mpcgpu_dtc_handle;
+
+int mpcgpu_dtc_create(const mpcgpu_dtc_problem *problem, int device, mpcgpu_dtc_handle **out);
+void mpcgpu_dtc_destroy(mpcgpu_dtc_handle *h);
+/* p: n x ny, m: n x nu, delta: n x ny, lambda: n x nu (weights are NOT squared here: Q = delta*I, W = lambda*I,
+ * DTC_GPC_WW.m:67-76); fr_num / fr_den: n x ny x MPCGPU_DTC_MAXF (descending powers of z, zero padded),
+ * fr_len: n x ny x 2 = {len(num), len(den)}.  ise: n x ny = sum_k (y_i - r_i)^2;  y: n x ny x nit, u: n x nu x nit
+ * (either may be NULL);  status: n. */
+int mpcgpu_dtc_eval_batch(mpcgpu_dtc_handle *h, int n, const int32_t *p, const int32_t *m, const double *delta,
+                          const double *lambda, const double *fr_num, const double *fr_den, const int32_t *fr_len,
+                          double *ise, double *y, double *u, int32_t *status);
+const char *mpcgpu_dtc_last_error(mpcgpu_dtc_handle *h);
+/* Host-only (no CUDA call): the candidate-independent polynomial tables the sweep is built from -- step responses
+ * (MatG.m:51), Diophantine F rows (diophantine.m:55-65), past-control rows (deltaUFree.m:36-57).  info: 64 ints
+ * {step_len, pmax, MAXNA, MAXCP, sum duM, sum(na+1)}, [8+i] na_i, [16+i] dmin_i, [24+i*nu+j] cp_ij, [48+j] duM_j;
+ * step: ny*nu*step_len, ftab: ny*(pmax+1)*MAXNA, ug: ny*nu*(pmax+1)*MAXCP.  Any output may be NULL. */
+int mpcgpu_dtc_host_tables(const mpcgpu_dtc_problem *problem, int32_t *info, double *step, double *ftab, double *ug);
+
 #ifdef __cplusplus
 }
 #endif

@@ -85,6 +85,13 @@ def load_library():
     lib.mpcgpu_cost_device_ptr.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int)]
     lib.mpcgpu_get_counters.argtypes = [C.c_void_p, C.POINTER(Counters)]
     lib.mpcgpu_measure_fp64_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
+    lib.mpcgpu_dtc_last_error.restype = C.c_char_p
+    lib.mpcgpu_dtc_last_error.argtypes = [C.c_void_p]
+    lib.mpcgpu_dtc_create.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
+    lib.mpcgpu_dtc_destroy.argtypes = [C.c_void_p]
+    lib.mpcgpu_dtc_destroy.restype = None
+    lib.mpcgpu_dtc_eval_batch.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 11
+    lib.mpcgpu_dtc_host_tables.argtypes = [C.c_void_p] * 5
     _lib = lib
     return lib
 
@@ -93,4 +100,6 @@ EXPORTED_SYMBOLS = [
     "mpcgpu_create", "mpcgpu_destroy", "mpcgpu_set_signals", "mpcgpu_eval_batch", "mpcgpu_upload", "mpcgpu_run",
     "mpcgpu_download", "mpcgpu_cost_device_ptr", "mpcgpu_get_counters", "mpcgpu_last_error", "mpcgpu_device_count",
     "mpcgpu_measure_fp64_peak",
+    "mpcgpu_dtc_create", "mpcgpu_dtc_destroy", "mpcgpu_dtc_eval_batch", "mpcgpu_dtc_last_error",
+    "mpcgpu_dtc_host_tables",
 ]

@@ -164,3 +164,66 @@ def test_edge_cases(ev3):
     assert g.shape == (3,) and h.size == 0
     F = mpcgpu.vns_cost(ev3, [24, 6, 24], [6, 2, 30], [1, 1, 1], [.1, .1, .1])
     assert np.isfinite(F[0]) and np.isinf(F[1]) and np.isinf(F[2])
+
+
+# ---------------------------------------------------------------------------------------------
+# DTC-GPC batched sweep (BASELINE.json configs[3])
+# ---------------------------------------------------------------------------------------------
+def _dtc_oracle(prob, p, m, dl, lm, alfa, raio):
+    from oracle import dtc_gpc_oracle as dorc
+    ys, us = [], []
+    for c in range(len(p)):
+        fr = dorc.mimofilter_Fr(prob.pnz, alfa[c], raio[c])
+        y, u = dorc.dtc_gpc_closed_loop(prob, p[c], m[c], dl[c], lm[c], fr)
+        ys.append(y); us.append(u)
+    return np.array(ys), np.array(us)
+
+
+@pytest.mark.parametrize("deltak,deltaL,min_tame", [(0.0, 0.0, 60), (0.1, 0.0, 48), (0.1, 0.3, 16)])
+def test_dtc_gpc_parity(deltak, deltaL, min_tame):
+    """GPU sweep vs the restated MATLAB on seeded candidates: ISE 1e-6 relative, y/u 1e-5 absolute.  Candidates
+    whose closed loop is unstable (the sweep's ranges include such tunings) are compared while they are
+    bounded: an exponentially growing loop amplifies rounding differences without limit."""
+    from mpcgpu.dtcgpc import woodberry_dtc, synthetic_dtc_population, DtcEvaluator
+    prob = woodberry_dtc(deltak=deltak, deltaL=deltaL)      # plant/model mismatch knobs of DTC_GPC_WW.m:18-19
+    ev = DtcEvaluator(prob, device=0)
+    p, m, dl, lm, alfa, raio = synthetic_dtc_population(prob, 64, seed=11)
+    out = ev.eval_batch(p, m, dl, lm, alfa=alfa, raio=raio, traj=True)
+    assert (out["status"] == 0).all()
+    y0, u0 = _dtc_oracle(prob, p, m, dl, lm, alfa, raio)
+    ise0 = ((y0 - prob.r[None]) ** 2).sum(axis=2)
+    tame = np.abs(y0).max(axis=(1, 2)) < 1e3
+    assert tame.sum() >= min_tame
+    assert np.abs(out["y"][tame] - y0[tame]).max() < TOL_TRAJ
+    assert np.abs(out["u"][tame] - u0[tame]).max() < TOL_TRAJ
+    rel = np.abs(out["ise"][tame] - ise0[tame]) / np.abs(ise0[tame])
+    assert rel.max() < 1e-6, rel.max()
+    ev.close()
+
+
+def test_dtc_gpc_golden_and_edges():
+    from mpcgpu.dtcgpc import woodberry_dtc, DtcEvaluator, dtc_gpc_ww
+    prob = woodberry_dtc()
+    ev = DtcEvaluator(prob, device=0)
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "oracle_golden_dtc.npz"))
+    out = ev.eval_batch(gold["p"], gold["m"], gold["delta"], gold["lam"], alfa=gold["alfa"], raio=gold["raio"], traj=True)
+    assert (out["status"] == 0).all()
+    assert np.abs(out["y"][:, :, ::4] - gold["y_sub"]).max() < TOL_TRAJ
+    assert np.abs(out["u"][:, :, ::4] - gold["u_sub"]).max() < TOL_TRAJ
+    assert (np.abs(out["ise"] - gold["ise"]) / gold["ise"]).max() < 1e-6
+    # the reference script's own run through the reference-shaped call
+    y, u = dtc_gpc_ww(prob, ev=ev)
+    assert np.abs(y[:, ::4] - gold["y_sub"][0]).max() < TOL_TRAJ
+    # illegal horizons are flagged, neighbours unaffected; cost-only call equals the trajectory call
+    p = np.array([[3, 3], [0, 3], [3, 3], [31, 3]], dtype=np.int32); m = np.array([[3, 3], [3, 3], [11, 3], [3, 3]], dtype=np.int32)
+    o2 = ev.eval_batch(p, m, np.ones((4, 2)), np.ones((4, 2)), alfa=0.7, raio=0.8)
+    assert list(o2["status"]) == [0, 4, 4, 4] and np.isnan(o2["ise"][1:]).all()
+    np.testing.assert_array_equal(o2["ise"][0], out["ise"][0])
+    # large population: deterministic and position-independent
+    from mpcgpu.dtcgpc import synthetic_dtc_population
+    P = synthetic_dtc_population(prob, 4096, seed=0)
+    a = ev.eval_batch(*P[:4], alfa=P[4], raio=P[5])
+    perm = np.random.default_rng(0).permutation(4096)
+    b = ev.eval_batch(*(x[perm] for x in P[:4]), alfa=P[4][perm], raio=P[5][perm])
+    assert np.array_equal(a["ise"][perm], b["ise"], equal_nan=True)
+    ev.close()
