@@ -25,9 +25,23 @@
 
 #define SIM_VIOL_TOL 1e-10
 #define SIM_DEP_TOL 1e-13
+#define SIM_REFRESH 96 /* Givens removals after which the active-set factor is rebuilt from W */
 #define SIM_CH 32 /* samples of r / yref / v staged into shared memory at a time */
 #define SIM_INF (__builtin_huge_val())
 #define SIM_FULL 0xffffffffu
+#ifdef MPC_SIMT_EMULATION   /* experiment switches, host emulation only */
+extern int g_sim_knob;
+extern long long g_sim_reappends, g_sim_rotations;
+#define SIM_KNOB(b) (g_sim_knob & (b))
+extern int g_sim_verbose;
+#include <cstdio>
+#define SIM_DBG(...) do { if (g_sim_verbose && lane == 0) { printf(__VA_ARGS__); } } while (0)
+#define SIM_DBGSET(tag) do { if (g_sim_verbose && lane == 0) { printf("%s q=%d:", tag, q); for (int a_ = 0; a_ < q; ++a_) printf(" %c%d.%d", "dDuU"[sm.act[a_] & 3], (sm.act[a_] >> 2) / P, (sm.act[a_] >> 2) % P); printf("\n"); } } while (0)
+#else
+#define SIM_KNOB(b) 0
+#define SIM_DBG(...) do { } while (0)
+#define SIM_DBGSET(tag) do { } while (0)
+#endif
 
 struct MpcRunOut {
     double *cost;                  // GAM: ny slots; VNS: 1 slot (partial sum of this run); RAW: nullptr
@@ -121,6 +135,7 @@ struct SimWarp {
     int q;          // uniform: carried active-set size
     unsigned long long n_con, n_it;
     int qmax;
+    int n_rot;      // uniform: Givens removals since the factor was last rebuilt from W
 
     __device__ __forceinline__ SimWarp(const MpcLayout &L_) : L(L_) {}
 
@@ -270,30 +285,97 @@ struct SimWarp {
             if (row[s] == (cid >> 2)) amask[s] |= (1 << (cid & 3));
         __syncwarp();
     }
-    // remove the active constraints flagged in sm.dflag (order of the rest kept), rebuild V / Li behind
-    __device__ __forceinline__ void drop_flagged() {
-        for (int a = 0; a < q; ++a) {  // clear mask bits (uniform loop)
-            if (sm.dflag[a]) {
-                const int cid = sm.act[a];
+    // Remove the active constraint at list position a (order of the rest kept) by Givens rotations.
+    // With Y = Li (S^-1 = Y'Y, Y lower triangular) and V = W N Y': rotating rows (k, k+1) of Y for
+    // k = a .. q-2 so that column a is annihilated in row k pushes that column's mass into the last row;
+    // every other row then has a zero in column a, i.e. it is a valid factor row of the reduced set once
+    // column a is deleted (columns right of a move one to the left, which also restores the triangle).
+    // The carried entry of column a at step k is the running norm sqrt(sum_{i=a..k} Y[i][a]^2), so all
+    // rotations come from one column and do not depend on each other; V's columns and Y's rows take the
+    // same rotations.  O((q-a)(R+q)) work, no pass over W.
+    __device__ __forceinline__ void remove_at(int a) {
+        const int nrot = q - 1 - a;
+        const int cid = sm.act[a];
+#pragma unroll
+        for (int s = 0; s < NSLOT; ++s)
+            if (row[s] == (cid >> 2)) amask[s] &= ~(1 << (cid & 3));
+        if (nrot > 0) {
+            // rotation coefficients (cx, cy) = (x, y) / hypot(x, y), kept in sm.g / sm.rr
+            for (int t = lane; t < nrot; t += 32) {
+                double ss = 0.0;
+                for (int i = a; i <= a + t; ++i) { const double v = Lirow(i)[a]; ss = fma(v, v, ss); }
+                const double y = Lirow(a + t + 1)[a];
+                const double inv = 1.0 / sqrt(fma(y, y, ss));
+                sm.g[t] = sqrt(ss) * inv;
+                sm.rr[t] = y * inv;
+            }
+            __syncwarp();
+            // V columns (lane owns rows) and Y columns (lane owns old column j, written to j or j-1)
+            double cv[NSLOT], cy0 = 0.0, cy1 = 0.0;
+            const int j0 = lane, j1 = lane + 32;
+#pragma unroll
+            for (int s = 0; s < NSLOT; ++s) cv[s] = row[s] < R ? Vcol(a)[row[s]] : 0.0;
+            if (j0 < a) cy0 = Lirow(a)[j0];
+            if (j1 < a) cy1 = Lirow(a)[j1];
+            for (int t = 0; t < nrot; ++t) {
+                const int k = a + t;
+                const double cx = sm.g[t], sy = sm.rr[t];
+                __syncwarp();   // row k was read by the previous step
+                const double *vsrc = Vcol(k + 1);
+                double *vdst = Vcol(k);
 #pragma unroll
                 for (int s = 0; s < NSLOT; ++s)
-                    if (row[s] == (cid >> 2)) amask[s] &= ~(1 << (cid & 3));
+                    if (row[s] < R) {
+                        const double o = vsrc[row[s]];
+                        vdst[row[s]] = cx * o - sy * cv[s];
+                        cv[s] = cx * cv[s] + sy * o;
+                    }
+                const double *ysrc = Lirow(k + 1);
+                double *ydst = Lirow(k);
+                if (j0 != a && j0 <= k + 1) {
+                    const double o = ysrc[j0];
+                    ydst[j0 < a ? j0 : j0 - 1] = cx * o - sy * cy0;
+                    cy0 = cx * cy0 + sy * o;
+                }
+                if (j1 <= k + 1) {   // j1 >= 32 > a is not required: guard both ways
+                    if (j1 != a) {
+                        const double o = ysrc[j1];
+                        ydst[j1 < a ? j1 : j1 - 1] = cx * o - sy * cy1;
+                        cy1 = cx * cy1 + sy * o;
+                    }
+                }
+            }
+            __syncwarp();
+            // compact the constraint list and its multipliers
+            int ca[2]; double cm[2];
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                const int pos = a + 1 + lane + 32 * s;
+                ca[s] = pos < q ? sm.act[pos] : 0;
+                cm[s] = pos < q ? sm.mu[pos] : 0.0;
+            }
+            __syncwarp();
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                const int pos = a + 1 + lane + 32 * s;
+                if (pos < q) { sm.act[pos - 1] = ca[s]; sm.mu[pos - 1] = cm[s]; }
             }
         }
         __syncwarp();
-        if (lane == 0) {
-            int qn = 0, first = -1;
-            for (int a = 0; a < q; ++a) {
-                if (sm.dflag[a]) { if (first < 0) first = a; }
-                else { sm.act[qn] = sm.act[a]; sm.mu[qn] = sm.mu[a]; ++qn; }
-            }
-            sm.misc[0] = qn; sm.misc[1] = first < 0 ? qn : first;
+        q -= 1;
+        n_rot += 1;
+#ifdef MPC_SIMT_EMULATION
+        if (lane == 0) g_sim_rotations += nrot;
+#endif
+    }
+    // remove every active constraint flagged in sm.dflag (highest position first, so that the positions of
+    // the ones still to go do not move)
+    __device__ __forceinline__ void drop_flagged() {
+        for (int a = q - 1; a >= 0; --a) {
+            const int fl = sm.dflag[a];
+            __syncwarp();
+            if (fl) remove_at(a);
         }
-        __syncwarp();
-        const int qn = sm.misc[0], first = sm.misc[1];
-        __syncwarp();
-        q = first;
-        rebuild(first, qn);
     }
     // Re-append the constraints stored at list positions [from, upto) behind the first `q` (= from on
     // entry) factor rows, skipping any that has become linearly dependent.  Leaves q = new size.
@@ -307,6 +389,9 @@ struct SimWarp {
             const double gam = ndot(cid, sm.w2, sm.w2sc);
             const double l2 = schur_vectors(q, sm.w2, sm.w2sc);
             const double rho = gam - l2;
+#ifdef MPC_SIMT_EMULATION
+            if (lane == 0) g_sim_reappends++;
+#endif
             if (rho > SIM_DEP_TOL * gam) {
                 add_V(q, sm.l, -1.0, wv);
                 commit(cid, q, rho, mua, wv);
@@ -353,6 +438,18 @@ struct SimWarp {
         // shifted by one sample (right while a ramp / transient plays out along the horizon).  The carried
         // factor makes the first guess cheap to score: solve for its multipliers, count the negative ones and,
         // if there are none, the constraints its solution violates.  Only a bad score pays for the rebuild.
+        SIM_DBGSET("entry");
+        if (q > 0 && n_rot > SIM_REFRESH) {   // bound the rounding drift of long rotation sequences
+            const int qn = q;
+            q = 0;
+            rebuild(0, qn);
+            n_rot = 0;
+        }
+        if (SIM_KNOB(1)) {
+            q = 0;
+#pragma unroll
+            for (int s = 0; s < NSLOT; ++s) amask[s] = 0;
+        }
         if (q > 0) {
             levels(lv);
             publish(lv);
@@ -384,7 +481,8 @@ struct SimWarp {
                 for (int s = 0; s < NSLOT; ++s) z[s] = zt[s];
             }
             __syncwarp();
-            if (bad > 1) { it += 1; shift_active_set(); }
+            SIM_DBG(" score bad=%d\n", bad);
+            if (bad > 1 && SIM_KNOB(4)) { it += 1; shift_active_set(); SIM_DBGSET(" shifted"); }
         }
         // ---- warm start on the carried set: mu = S^-1 (b_A - N_A' z_unc), shed negative multipliers ----
         while (q > 0) {
@@ -397,6 +495,13 @@ struct SimWarp {
             for (int a = lane; a < q; a += 32) mumax = fmax(mumax, fabs(sm.mu[a]));
             mumax = sim_wmax(mumax);
             int nd_ = 0;
+            if (SIM_KNOB(8)) {   // experiment: shed only the most negative multiplier per round
+                double mv = 0.0; int mi = -1;
+                for (int a = lane; a < q; a += 32) if (sm.mu[a] < mv) { mv = sm.mu[a]; mi = a; }
+                sim_wargmin(mv, mi);
+                for (int a = lane; a < q; a += 32) sm.dflag[a] = (a == mi) && (mv < -1e-12 * mumax);
+                nd_ = mi >= 0 && (mv < -1e-12 * mumax);
+            } else
             for (int a = lane; a < q; a += 32) {
                 const int fl = sm.mu[a] < -1e-12 * mumax;
                 sm.dflag[a] = fl;
@@ -407,6 +512,7 @@ struct SimWarp {
             if (!nd_) break;
             it += 1;
             drop_flagged();
+            SIM_DBGSET(" shed-negative");
         }
         if (q > 0) {  // z = z_unc + V l  (l = Li g is still in sm.l)
             add_V(q, sm.l, 1.0, z);
@@ -430,7 +536,7 @@ struct SimWarp {
                 }
             }
 #ifndef SIM_PIVOT_MOST_VIOLATED
-            {   // pivot rule: among the violated constraints take the EARLIEST horizon index first (then the
+            if (!SIM_KNOB(2)) {   // pivot rule: among the violated constraints take the EARLIEST horizon index first (then the
                 // most violated).  Any violated constraint is a valid Goldfarb-Idnani pivot; walking the
                 // horizon in time order follows how rate/level saturation propagates and avoids most of the
                 // add/drop churn of the most-violated rule (measured: 233 -> see DESIGN.md).
@@ -443,6 +549,7 @@ struct SimWarp {
             sim_wargmin(bv, bi);
             if (bi < 0) break;
             const int p = bi;
+            SIM_DBG("  pivot %c%d.%d viol %.3e (q=%d)\n", "dDuU"[p & 3], (p >> 2) / P, (p >> 2) % P, bv, q);
             double sp = bv, mu_p = 0.0;
             double wv[NSLOT];
             w_times_normal(p, wv, sm.w, sm.wsc);
@@ -481,6 +588,7 @@ struct SimWarp {
                 }
                 mu_p += t;
                 __syncwarp();
+                if (!full) SIM_DBG("    partial step t=%.3e drop pos %d (%c%d.%d) dependent=%d\n", t, l1, "dDuU"[sm.act[l1 < 0 ? 0 : l1] & 3], (sm.act[l1 < 0 ? 0 : l1] >> 2) / P, (sm.act[l1 < 0 ? 0 : l1] >> 2) % P, dependent);
                 if (full) {
                     commit(p, q, rho, mu_p, dir);
                     q += 1;
@@ -508,6 +616,7 @@ struct SimWarp {
         }
         n_it += it;
         if (q > qmax) qmax = q;
+        SIM_DBGSET("final");
         return 0;
     }
 
@@ -593,7 +702,7 @@ __device__ __forceinline__ int sim_run(const MpcLayout &L, const MpcTables &T, i
         sm.chd = ip; ip += nch; sm.chj = ip; ip += nch; sm.role = ip; ip += nst;
         sm.act = ip; ip += R; sm.dflag = ip; ip += R; sm.misc = ip;
     }
-    wp.gscr = gscr; wp.W = Wg; wp.lane = lane; wp.m = m; wp.q = 0; wp.n_con = 0; wp.n_it = 0; wp.qmax = 0;
+    wp.gscr = gscr; wp.W = Wg; wp.lane = lane; wp.m = m; wp.q = 0; wp.n_con = 0; wp.n_it = 0; wp.qmax = 0; wp.n_rot = 0;
 #pragma unroll
     for (int s = 0; s < NSLOT; ++s) {
         const int r = s * 32 + lane;
@@ -755,6 +864,11 @@ __device__ __forceinline__ int sim_run(const MpcLayout &L, const MpcTables &T, i
         const double *sigrow = sm.sig + (size_t)(k & (SIM_CH - 1)) * nsig;
         build_st(sigrow, k, true);
         const unsigned long long it_before = wp.n_it;
+#ifdef MPC_SIMT_EMULATION
+        if (lane == 0) g_sim_verbose = (g_sim_knob >> 16) && k >= (g_sim_knob >> 16) && k < (g_sim_knob >> 16) + 2;
+        if (g_sim_verbose && lane == 0) printf("=== sample %d\n", k);
+        __syncwarp();
+#endif
         const int rc = wp.controller_move();
         if (rc) status = rc;
         if (out.trace && lane == 0) { out.trace[2 * k] = (int)(wp.n_it - it_before); out.trace[2 * k + 1] = wp.q; }

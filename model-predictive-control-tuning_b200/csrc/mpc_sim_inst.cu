@@ -1,0 +1,17 @@
+// mpc_sim_inst.cu -- instantiates k_sim<SIM_NU, P> for P = 4, 8, 16 (compiled once per SIM_NU = 1..4).
+#include "mpc_sim_kernel.cuh"
+
+#ifndef SIM_NU
+#error "compile with -DSIM_NU=1..4"
+#endif
+#define SIM_CAT2(a, b) a##b
+#define SIM_CAT(a, b) SIM_CAT2(a, b)
+
+sim_kernel_t SIM_CAT(sim_kernel_nu, SIM_NU)(int P) {
+    switch (P) {
+        case 4: return k_sim<SIM_NU, 4>;
+        case 8: return k_sim<SIM_NU, 8>;
+        case 16: return k_sim<SIM_NU, 16>;
+    }
+    return nullptr;
+}

@@ -17,7 +17,7 @@
 
 #include "../../include/mpcgpu.h"
 #include "mpc_core.cuh"
-#include "mpc_sim.cuh"
+#include "mpc_sim_kernel.cuh"
 #include "mpc_tables.h"
 
 #define NSTREAM 4  /* >= number of size buckets (P = 4, 8, 16): every bucket runs concurrently */
@@ -36,25 +36,6 @@ static std::string g_create_error;
         }                                                                                          \
     } while (0)
 
-struct DevCand {
-    const int *N, *Nu;
-    const double *delta, *lambda;
-    const long long *offM, *offW;
-    double *M, *W;
-    int *bstatus;  // builder status per candidate
-    double *scratch;  // per-run spill area of the closed-loop kernel (V / Li beyond QC)
-    long long scratch_stride;
-};
-
-struct DevOut {
-    double *cost;   // GAM: n*ny ; VNS: n
-    double *part;   // VNS partial sums n*runs
-    int *status;    // n
-    unsigned long long *counters;  // [0] constrained QPs [1] active-set iterations
-    double *y, *u, *ys, *uopt;     // optional trajectories
-    unsigned long long *diag;      // optional per-run diagnostics (4 per run)
-};
-
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(BUILD_THREADS) k_build(const MpcLayout L, const MpcTables T, const int *order,
                                                          int count, DevCand C) {
@@ -69,49 +50,12 @@ __global__ void __launch_bounds__(BUILD_THREADS) k_build(const MpcLayout L, cons
     if (threadIdx.x == 0) C.bstatus[c] = st;
 }
 
-// One warp per (candidate, run).  mode: 0 RAW, 1 GAM, 2 VNS.
-template <int NU, int P>
-__global__ void __launch_bounds__(32) k_sim(const MpcLayout L, const MpcTables T, const int *order, int count, int runs,
-                                            int mode, int square, long long item0, DevCand C, DevOut O) {
-    extern __shared__ double smem_s[];
-    const int item = blockIdx.x;
-    if (item >= count * runs) return;
-    const int c = order[item / runs];
-    const int run = item - (item / runs) * runs;
-    const int m = C.Nu[c];
-    const int ny = L.ny, nit = L.nit;
-    if (C.bstatus[c] != 0) {
-        if ((threadIdx.x & 31) == 0) {
-            atomicMax(O.status + c, C.bstatus[c]);
-            if (mode == 1) for (int i = 0; i < ny; ++i) O.cost[(size_t)c * ny + i] = NAN;
-            if (mode == 2) O.part[(size_t)c * runs + run] = NAN;
-        }
-        return;
-    }
-    MpcRunOut out;
-    out.cost = mode == 1 ? O.cost + (size_t)c * ny : (mode == 2 ? O.part + (size_t)c * runs + run : nullptr);
-    out.y = O.y ? O.y + (size_t)c * ny * nit : nullptr;
-    out.u = O.u ? O.u + (size_t)c * NU * nit : nullptr;
-    out.ys = O.ys ? O.ys + (size_t)c * ny * nit : nullptr;
-    out.uopt = O.uopt ? O.uopt + (size_t)c * NU * nit : nullptr;
-    out.counters = O.counters;
-    out.diag = O.diag ? O.diag + 4 * ((size_t)c * runs + run) : nullptr;
-    out.trace = nullptr;
-    const long long t_start = clock64();
-    const int sel = mode == 2 ? (square ? run : -1) : -2;
-    double *gscr = C.scratch ? C.scratch + (size_t)(item0 + item) * C.scratch_stride : nullptr;
-    const int st = sim_run<NU, P>(L, T, m, C.M + C.offM[c], C.W + C.offW[c], mode, sel, smem_s, gscr, out);
-    if (st != 0 && (threadIdx.x & 31) == 0) atomicMax(O.status + c, st);
-    if (out.diag && (threadIdx.x & 31) == 0) out.diag[3] = (unsigned long long)(clock64() - t_start);
-}
-
-typedef void (*sim_kernel_t)(const MpcLayout, const MpcTables, const int *, int, int, int, int, long long, DevCand, DevOut);
 static sim_kernel_t sim_kernel(int nu, int P) {
-    switch (nu * 100 + P) {
-        case 104: return k_sim<1, 4>;   case 108: return k_sim<1, 8>;   case 116: return k_sim<1, 16>;
-        case 204: return k_sim<2, 4>;   case 208: return k_sim<2, 8>;   case 216: return k_sim<2, 16>;
-        case 304: return k_sim<3, 4>;   case 308: return k_sim<3, 8>;   case 316: return k_sim<3, 16>;
-        case 404: return k_sim<4, 4>;   case 408: return k_sim<4, 8>;   case 416: return k_sim<4, 16>;
+    switch (nu) {
+        case 1: return sim_kernel_nu1(P);
+        case 2: return sim_kernel_nu2(P);
+        case 3: return sim_kernel_nu3(P);
+        case 4: return sim_kernel_nu4(P);
     }
     return nullptr;
 }

@@ -5,6 +5,13 @@
 // libmpcgpu.so and the product never loads it.
 #define MPC_HOST_EMULATION 1
 #include "simt.h"
+int g_sim_knob = 0;
+int g_sim_verbose = 0;
+extern "C" void emu_set_verbose(int v) { g_sim_verbose = v; }
+long long g_sim_reappends = 0, g_sim_rotations = 0;
+extern "C" long long emu_rotations() { long long r = g_sim_rotations; g_sim_rotations = 0; return r; }
+extern "C" void emu_set_knob(int k) { g_sim_knob = k; }
+extern "C" long long emu_reappends() { long long r = g_sim_reappends; g_sim_reappends = 0; return r; }
 
 #include <cmath>
 #include <cstdlib>
