@@ -53,6 +53,12 @@ struct MpcRunOut {
 
 static MPC_HD int sim_pad(int m) { return m <= 4 ? 4 : (m <= 8 ? 8 : 16); }
 static MPC_HD int sim_qc(int R) { return R <= 24 ? R : 24; }
+// M (nst x R) lives in shared memory for the small buckets; for P = 16 it stays in global memory (read-only,
+// L1/L2 resident, loads independent of the state) so that twice as many runs fit on an SM.
+#ifndef SIM_M_GLOBAL_P
+#define SIM_M_GLOBAL_P 16
+#endif
+static MPC_HD bool sim_m_in_smem(int P) { return P < SIM_M_GLOBAL_P; }
 static MPC_HD int sim_hl(const MpcLayout &L) {
     int h = 1;
     for (int j = 0; j < L.nw; ++j) h = L.hlen[j] > h ? L.hlen[j] : h;
@@ -65,7 +71,7 @@ static MPC_HD size_t sim_scratch_doubles(int R) {
 }
 static MPC_HD size_t sim_smem_doubles(const MpcLayout &L, int nu, int P) {
     const int R = nu * P, qc = sim_qc(R), nch = L.ny * L.nw, HL = sim_hl(L);
-    size_t n = (size_t)L.nst * R;            // M
+    size_t n = sim_m_in_smem(P) ? (size_t)L.nst * R : 0;   // M
     n += (L.nst + 1) & ~1;                    // st
     n += 2 * nch;                             // x, xol
     n += (size_t)L.nw * HL;                   // hist
@@ -124,6 +130,7 @@ struct SimWarp {
     SimSm sm;
     double *gscr;   // per-run global scratch (V columns / Li rows beyond QC), may be nullptr when QC == R
     const double *W;
+    const double *Mp;   // M: shared memory (P < 16) or global
     int lane, m;
     // per-lane row data
     int row[NSLOT];
@@ -403,41 +410,13 @@ struct SimWarp {
             }
         }
     }
-    // Receding horizon: the plan computed at k-1 is one sample older at k, so the carried constraint on
-    // (j, c) becomes the guess (j, c-1); those on c == 0 have been applied and leave the set.
-    __device__ __forceinline__ void shift_active_set() {
-        if (lane == 0) {
-            int qn = 0;
-            for (int a = 0; a < q; ++a) {
-                const int cid = sm.act[a], r = cid >> 2;
-                if ((r & (P - 1)) > 0) { sm.act[qn] = (cid & 3) | ((r - 1) << 2); sm.mu[qn] = sm.mu[a]; ++qn; }
-            }
-            sm.misc[0] = qn;
-        }
-        __syncwarp();
-        const int qn = sm.misc[0];
-#pragma unroll
-        for (int s = 0; s < NSLOT; ++s) amask[s] = 0;
-        for (int a = 0; a < qn; ++a) {
-            const int cid = sm.act[a];
-#pragma unroll
-            for (int s = 0; s < NSLOT; ++s)
-                if (row[s] == (cid >> 2)) amask[s] |= (1 << (cid & 3));
-        }
-        __syncwarp();
-        q = 0;
-        rebuild(0, qn);
-    }
-
-    // Dual active-set QP, warm-started from the carried set.  z (registers) in: z_unc, out: optimum.
+    // Dual active-set QP, warm-started from the carried set AS IT IS.  (Shifting the set by one sample to follow the
+    // receding horizon was measured to cost more than it saves: the shifted guess sheds most of its members
+    // through negative multipliers and has to be rebuilt from W.)  z (registers) in: z_unc, out: optimum.
     __device__ __forceinline__ int qp_solve() {
         int it = 0;
         const int itmax = 20 * (NU * m + 10);
         double lv[NSLOT];
-        // ---- which guess?  The carried set as it is (right when the saturation pattern is stationary) or
-        // shifted by one sample (right while a ramp / transient plays out along the horizon).  The carried
-        // factor makes the first guess cheap to score: solve for its multipliers, count the negative ones and,
-        // if there are none, the constraints its solution violates.  Only a bad score pays for the rebuild.
         SIM_DBGSET("entry");
         if (q > 0 && n_rot > SIM_REFRESH) {   // bound the rounding drift of long rotation sequences
             const int qn = q;
@@ -449,40 +428,6 @@ struct SimWarp {
             q = 0;
 #pragma unroll
             for (int s = 0; s < NSLOT; ++s) amask[s] = 0;
-        }
-        if (q > 0) {
-            levels(lv);
-            publish(lv);
-            for (int a = lane; a < q; a += 32) sm.g[a] = -slack_of(sm.act[a]);
-            __syncwarp();
-            schur_solve(q, sm.mu);
-            double mumax = 0.0;
-            for (int a = lane; a < q; a += 32) mumax = fmax(mumax, fabs(sm.mu[a]));
-            mumax = sim_wmax(mumax);
-            int bad = 0;
-            for (int a0 = 0; a0 < q; a0 += 32) {
-                const int a = a0 + lane;
-                bad += __popc(__ballot_sync(SIM_FULL, a < q && sm.mu[a] < -1e-12 * mumax));
-            }
-            if (bad == 0) {
-                double zt[NSLOT];
-#pragma unroll
-                for (int s = 0; s < NSLOT; ++s) zt[s] = z[s];
-                add_V(q, sm.l, 1.0, z);
-                levels(lv);
-#pragma unroll
-                for (int s = 0; s < NSLOT; ++s) {
-                    const double sl[4] = {z[s] - dlo[s], dhi[s] - z[s], lv[s] - ulo[s], uhi[s] - lv[s]};
-#pragma unroll
-                    for (int type = 0; type < 4; ++type)
-                        bad += __popc(__ballot_sync(SIM_FULL, valid[s] && !(amask[s] & (1 << type)) && sl[type] < -SIM_VIOL_TOL));
-                }
-#pragma unroll
-                for (int s = 0; s < NSLOT; ++s) z[s] = zt[s];
-            }
-            __syncwarp();
-            SIM_DBG(" score bad=%d\n", bad);
-            if (bad > 1 && SIM_KNOB(4)) { it += 1; shift_active_set(); SIM_DBGSET(" shifted"); }
         }
         // ---- warm start on the carried set: mu = S^-1 (b_A - N_A' z_unc), shed negative multipliers ----
         while (q > 0) {
@@ -625,7 +570,7 @@ struct SimWarp {
         const int nst = L.nst;
 #pragma unroll
         for (int s = 0; s < NSLOT; ++s) z[s] = 0.0;
-        {
+        if (sim_m_in_smem(P)) {
             double acc0[NSLOT], acc1[NSLOT];
 #pragma unroll
             for (int s = 0; s < NSLOT; ++s) { acc0[s] = 0.0; acc1[s] = 0.0; }
@@ -645,6 +590,35 @@ struct SimWarp {
 #pragma unroll
                 for (int s = 0; s < NSLOT; ++s)
                     if (row[s] < R) acc0[s] = fma(sm.M[(size_t)sg * R + row[s]], s0, acc0[s]);
+            }
+#pragma unroll
+            for (int s = 0; s < NSLOT; ++s) z[s] = acc0[s] + acc1[s];
+        } else {
+            // M from global memory: eight columns (8 * NSLOT independent loads per lane) in flight at a time
+            double acc0[NSLOT], acc1[NSLOT];
+#pragma unroll
+            for (int s = 0; s < NSLOT; ++s) { acc0[s] = 0.0; acc1[s] = 0.0; }
+            const double *mp = Mp + lane;
+            int sg = 0;
+            for (; sg + 8 <= nst; sg += 8) {
+                double mv[8][NSLOT];
+#pragma unroll
+                for (int e = 0; e < 8; ++e)
+#pragma unroll
+                    for (int s = 0; s < NSLOT; ++s)
+                        mv[e][s] = (s * 32 + lane < R) ? __ldg(mp + (size_t)(sg + e) * R + s * 32) : 0.0;
+#pragma unroll
+                for (int e = 0; e < 8; e += 2) {
+                    const double s0 = sm.st[sg + e], s1 = sm.st[sg + e + 1];
+#pragma unroll
+                    for (int s = 0; s < NSLOT; ++s) { acc0[s] = fma(mv[e][s], s0, acc0[s]); acc1[s] = fma(mv[e + 1][s], s1, acc1[s]); }
+                }
+            }
+            for (; sg < nst; ++sg) {
+                const double s0 = sm.st[sg];
+#pragma unroll
+                for (int s = 0; s < NSLOT; ++s)
+                    if (s * 32 + lane < R) acc0[s] = fma(__ldg(mp + (size_t)sg * R + s * 32), s0, acc0[s]);
             }
 #pragma unroll
             for (int s = 0; s < NSLOT; ++s) z[s] = acc0[s] + acc1[s];
@@ -685,7 +659,7 @@ __device__ __forceinline__ int sim_run(const MpcLayout &L, const MpcTables &T, i
     SimSm &sm = wp.sm;
     {   // carve shared memory
         double *p = smem;
-        sm.M = p; p += (size_t)nst * R;
+        sm.M = p; if (sim_m_in_smem(P)) p += (size_t)nst * R;
         sm.st = p; p += (nst + 1) & ~1;
         sm.x = p; p += nch;
         sm.xol = p; p += nch;
@@ -720,7 +694,8 @@ __device__ __forceinline__ int sim_run(const MpcLayout &L, const MpcTables &T, i
 #pragma unroll
     for (int j = 0; j < NU; ++j) wp.u[j] = 0.0;
     // ---- one-time staging ----
-    for (int i = lane; i < nst * R; i += 32) sm.M[i] = Mg[i];
+    if (sim_m_in_smem(P)) { for (int i = lane; i < nst * R; i += 32) sm.M[i] = Mg[i]; }
+    wp.Mp = sim_m_in_smem(P) ? sm.M : Mg;
     for (int ch = lane; ch < nch; ch += 32) {
         sm.cha[ch] = L.a[ch]; sm.chb0[ch] = L.b0[ch]; sm.chb1[ch] = L.b1[ch]; sm.chg[ch] = L.gain[ch];
         sm.chd[ch] = L.d[ch]; sm.chj[ch] = ch % nw;

@@ -11,19 +11,28 @@ out = open(sys.argv[4], "w") if len(sys.argv) > 4 else sys.stdout
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "model-predictive-control-tuning_b200", "csrc")
 tmp = tempfile.mkdtemp()
-subprocess.run(["cuobjdump", "-xelf", "all", os.path.join(CSRC, "libmpcgpu.so")], cwd=tmp, capture_output=True)
-cubin = [f for f in os.listdir(tmp) if f.startswith("mpcgpu.") and f.endswith(".cubin")][0]
-dis = subprocess.run(["nvdisasm", "-g", "-c", cubin], cwd=tmp, capture_output=True, text=True).stdout.split("\n")
-src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + kre, "--launch-skip", "0",
-                      "--launch-count", "1"], capture_output=True, text=True).stdout
+dis = None
+objs = sorted(os.path.join(CSRC, "build", f) for f in os.listdir(os.path.join(CSRC, "build")) if f.endswith(".o"))
+for k, obj in enumerate(objs):   # one object (and cubin) per translation unit; the .so is linked from these
+    d = os.path.join(tmp, str(k)); os.mkdir(d)
+    subprocess.run(["cuobjdump", "-xelf", "all", obj], cwd=d, capture_output=True)
+    for cubin in os.listdir(d):
+        txt = subprocess.run(["nvdisasm", "-g", "-c", cubin], cwd=d, capture_output=True, text=True).stdout
+        if ".text." + mangled in txt:
+            dis = txt.split("\n")
+    if dis:
+        break
+assert dis is not None, "kernel not found in libmpcgpu.so"
+src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(src.split("\n")))
-hdr = rows[1]
+# the export holds one block per profiled launch: a "Kernel Name" row, a header row, then one row per SASS instruction
+starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name" and re.search(kre, r[1])]
+assert starts, "no launch matches " + kre
+hdr = rows[starts[0] + 1]
 data = []
-for r in rows[2:]:
+for r in rows[starts[0] + 2:]:
     if len(r) != len(hdr) or not r[0].startswith("0x"):
-        if data:
-            break
-        continue
+        break
     data.append(r)
 iS, iI = hdr.index("# Samples"), hdr.index("Instructions Executed")
 start = [i for i, l in enumerate(dis) if l.startswith(".text." + mangled)][0]
