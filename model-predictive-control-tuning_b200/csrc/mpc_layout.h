@@ -38,6 +38,10 @@ struct MpcLayout {
     double umin[MPC_MAXU], umax[MPC_MAXU], dumin[MPC_MAXU], dumax[MPC_MAXU];
     double su[MPC_MAXU], sy[MPC_MAXY];
     double gain[MPC_MAXY * MPC_MAXW];
+    // soft output constraints (T4 of the oracle header): ymin_i - eps*emin_i <= y_i <= ymax_i + eps*emax_i,
+    // emin/emax = OV(i).MinECR/MaxECR * ScaleFactor; rho_ecr = Weights.ECR
+    double ymin[MPC_MAXY], ymax[MPC_MAXY], emin[MPC_MAXY], emax[MPC_MAXY];
+    double rho_ecr;
 };
 
 // Candidate-independent prediction tables (device or host pointers, all fp64):
@@ -54,6 +58,9 @@ struct MpcTables {
     const double *r;     // nit x ny
     const double *v;     // nit x nd
     const double *yref;  // ny x nit
+    const double *ST;    // step responses of the MV channels s_ij(n): [(i*nu+j)*st_stride + n]
+    const double *PA;    // channel pole powers a_ch^n: [ch*(pmax+1) + n]
+    int st_stride;
 };
 
 static MPC_HD long long mpc_tg_index(const MpcLayout &L, int i, int D, int Lh, int j, int j2) {

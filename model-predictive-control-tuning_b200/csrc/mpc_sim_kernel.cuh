@@ -7,6 +7,7 @@
 
 #include "../../include/mpcgpu.h"
 #include "mpc_sim.cuh"
+#include "mpc_soft.cuh"
 
 struct DevCand {
     const int *N, *Nu;
@@ -65,8 +66,46 @@ __global__ void __launch_bounds__(32) k_sim(const MpcLayout L, const MpcTables T
 }
 
 
+// One CTA per (candidate, run): plants with soft output constraints (mpc_soft.cuh).
+template <int NU, int P>
+__global__ void __launch_bounds__(SOFT_THREADS) k_soft(const MpcLayout L, const MpcTables T, const int *order, int count, int runs,
+                                                       int mode, int square, long long item0, DevCand C, DevOut O) {
+    extern __shared__ double smem_f[];
+    const int item = blockIdx.x;
+    if (item >= count * runs) return;
+    const int c = order[item / runs];
+    const int run = item - (item / runs) * runs;
+    const int ny = L.ny, nit = L.nit;
+    if (C.bstatus[c] != 0) {
+        if (threadIdx.x == 0) {
+            atomicMax(O.status + c, C.bstatus[c]);
+            if (mode == 1) for (int i = 0; i < ny; ++i) O.cost[(size_t)c * ny + i] = NAN;
+            if (mode == 2) O.part[(size_t)c * runs + run] = NAN;
+        }
+        return;
+    }
+    MpcRunOut out;
+    out.cost = mode == 1 ? O.cost + (size_t)c * ny : (mode == 2 ? O.part + (size_t)c * runs + run : nullptr);
+    out.y = O.y ? O.y + (size_t)c * ny * nit : nullptr;
+    out.u = O.u ? O.u + (size_t)c * NU * nit : nullptr;
+    out.ys = O.ys ? O.ys + (size_t)c * ny * nit : nullptr;
+    out.uopt = O.uopt ? O.uopt + (size_t)c * NU * nit : nullptr;
+    out.counters = O.counters;
+    out.diag = O.diag ? O.diag + 4 * ((size_t)c * runs + run) : nullptr;
+    out.trace = nullptr;
+    const long long t_start = clock64();
+    const int sel = mode == 2 ? (square ? run : -1) : -2;
+    const int st = soft_run<NU, P>(L, T, C.N[c], C.Nu[c], C.M + C.offM[c], C.W + C.offW[c], mode, sel, smem_f, out);
+    if (st != 0 && threadIdx.x == 0) atomicMax(O.status + c, st);
+    if (out.diag && threadIdx.x == 0) out.diag[3] = (unsigned long long)(clock64() - t_start);
+}
+
 typedef void (*sim_kernel_t)(const MpcLayout, const MpcTables, const int *, int, int, int, int, long long, DevCand, DevOut);
 sim_kernel_t sim_kernel_nu1(int P);
 sim_kernel_t sim_kernel_nu2(int P);
 sim_kernel_t sim_kernel_nu3(int P);
 sim_kernel_t sim_kernel_nu4(int P);
+sim_kernel_t soft_kernel_nu1(int P);
+sim_kernel_t soft_kernel_nu2(int P);
+sim_kernel_t soft_kernel_nu3(int P);
+sim_kernel_t soft_kernel_nu4(int P);

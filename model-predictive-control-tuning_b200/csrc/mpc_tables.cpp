@@ -52,7 +52,12 @@ std::string mpc_build_tables(const mpcgpu_problem &pb, MpcHostTables &out) {
         if (!(pb.su[j] > 0)) return "MV ScaleFactor must be > 0";
     }
     L.has_ov_bounds = 0;
+    L.rho_ecr = pb.rho_ecr;
     for (int i = 0; i < ny; ++i) {
+        L.ymin[i] = pb.ymin ? pb.ymin[i] : -INFINITY;
+        L.ymax[i] = pb.ymax ? pb.ymax[i] : INFINITY;
+        L.emin[i] = (pb.ecr_min ? pb.ecr_min[i] : 1.0) * pb.sy[i];
+        L.emax[i] = (pb.ecr_max ? pb.ecr_max[i] : 1.0) * pb.sy[i];
         L.sy[i] = pb.sy[i];
         if (!(pb.sy[i] > 0)) return "OV ScaleFactor must be > 0";
         if (pb.ymin && std::isfinite(pb.ymin[i])) L.has_ov_bounds = 1;
@@ -94,6 +99,9 @@ std::string mpc_build_tables(const mpcgpu_problem &pb, MpcHostTables &out) {
             for (int n = 1; n <= T; ++n) s[n] = chan_step(pb, nw, i, j, s[n - 1], n);
         }
     auto S = [&](int i, int j, int n) -> double { return out.step[((size_t)i * nu + j) * (T + 1) + n]; };
+    out.pa.assign((size_t)ny * nw * (P + 1), 1.0);
+    for (int c = 0; c < ny * nw; ++c)
+        for (int n = 1; n <= P; ++n) out.pa[(size_t)c * (P + 1) + n] = out.pa[(size_t)c * (P + 1) + n - 1] * pb.a[c];
     // S1
     out.S1.assign((size_t)ny * nu * (P + 1), 0.0);
     for (int i = 0; i < ny; ++i)

@@ -9,7 +9,8 @@
 struct MpcHostTables {
     MpcLayout L;
     std::vector<double> TG, TK, S1;
-    std::vector<double> step;  // s_ij(n), [i][j][n], n = 0..pmax+mmax
+    std::vector<double> step;  // s_ij(n), [i][j][n], n = 0..pmax+mmax+1 (stride pmax+mmax+2)
+    std::vector<double> pa;    // a_ch^n, [ch][n], n = 0..pmax
     std::vector<double> r, v, yref;
     std::vector<int> dmin;
 };

@@ -50,6 +50,15 @@ __global__ void __launch_bounds__(BUILD_THREADS) k_build(const MpcLayout L, cons
     if (threadIdx.x == 0) C.bstatus[c] = st;
 }
 
+static sim_kernel_t soft_kernel(int nu, int P) {
+    switch (nu) {
+        case 1: return soft_kernel_nu1(P);
+        case 2: return soft_kernel_nu2(P);
+        case 3: return soft_kernel_nu3(P);
+        case 4: return soft_kernel_nu4(P);
+    }
+    return nullptr;
+}
 static sim_kernel_t sim_kernel(int nu, int P) {
     switch (nu) {
         case 1: return sim_kernel_nu1(P);
@@ -126,7 +135,7 @@ struct mpcgpu_handle {
     cudaStream_t stream = nullptr;          // own stream for eval_batch / upload / download
     cudaStream_t pool[NSTREAM] = {};
     cudaEvent_t ev_fork = nullptr, ev_join[NSTREAM] = {}, ev_t0 = nullptr, ev_t1 = nullptr, ev_t2 = nullptr;
-    DBuf<double> dTG, dTK, dS1, dR, dV, dYref;
+    DBuf<double> dTG, dTK, dS1, dR, dV, dYref, dST, dPA;
     // population
     int n = 0;
     bool uploaded = false, ran = false;
@@ -151,6 +160,7 @@ struct mpcgpu_handle {
 static MpcTables dev_tables(mpcgpu_handle *h) {
     MpcTables T;
     T.TG = h->dTG.p; T.TK = h->dTK.p; T.S1 = h->dS1.p; T.r = h->dR.p; T.v = h->dV.p; T.yref = h->dYref.p;
+    T.ST = h->dST.p; T.PA = h->dPA.p; T.st_stride = h->ht.L.pmax + h->ht.L.mmax + 2;
     return T;
 }
 
@@ -216,6 +226,10 @@ extern "C" int mpcgpu_create(const mpcgpu_problem *problem, int device, mpcgpu_h
     if ((ce = h->dTG.ensure(t.TG.size())) != cudaSuccess) return fail("alloc TG", ce);
     if ((ce = h->dTK.ensure(t.TK.size())) != cudaSuccess) return fail("alloc TK", ce);
     if ((ce = h->dS1.ensure(t.S1.size())) != cudaSuccess) return fail("alloc S1", ce);
+    if ((ce = h->dST.ensure(t.step.size())) != cudaSuccess) return fail("alloc ST", ce);
+    if ((ce = h->dPA.ensure(t.pa.size())) != cudaSuccess) return fail("alloc PA", ce);
+    cudaMemcpy(h->dST.p, t.step.data(), t.step.size() * sizeof(double), cudaMemcpyHostToDevice);
+    cudaMemcpy(h->dPA.p, t.pa.data(), t.pa.size() * sizeof(double), cudaMemcpyHostToDevice);
     cudaMemcpy(h->dTG.p, t.TG.data(), t.TG.size() * sizeof(double), cudaMemcpyHostToDevice);
     cudaMemcpy(h->dTK.p, t.TK.data(), t.TK.size() * sizeof(double), cudaMemcpyHostToDevice);
     ce = cudaMemcpy(h->dS1.p, t.S1.data(), t.S1.size() * sizeof(double), cudaMemcpyHostToDevice);
@@ -223,22 +237,30 @@ extern "C" int mpcgpu_create(const mpcgpu_problem *problem, int device, mpcgpu_h
     if (upload_signals(h) != MPCGPU_OK) { g_create_error = h->err; mpcgpu_destroy(h); return MPCGPU_ERR_CUDA; }
     if ((ce = h->dCounters.ensure(4)) != cudaSuccess) return fail("alloc counters", ce);
     // allow large dynamic shared memory on both kernels
-    cudaFuncSetAttribute(k_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin);
-    for (int P = 4; P <= 16; P *= 2)
+    // (k_build also has a few bytes of static shared memory: dynamic + static must stay within the opt-in limit)
+    if ((ce = cudaFuncSetAttribute(k_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin - 1024)) != cudaSuccess)
+        return fail("cudaFuncSetAttribute(k_build)", ce);
+    for (int P = 4; P <= 16; P *= 2) {
         cudaFuncSetAttribute(sim_kernel(t.L.nu, P), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin);
+        cudaFuncSetAttribute(soft_kernel(t.L.nu, P), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin);
+    }
     // check the largest footprints fit
     const size_t sb = mpc_builder_smem_doubles(t.L.nu * t.L.mmax, t.L.nst) * sizeof(double);
     const size_t ss = sim_smem_doubles(t.L, t.L.nu, sim_pad(t.L.mmax)) * sizeof(double);
-    if (sb > h->smem_optin || ss > h->smem_optin) {
+    if (sb > h->smem_optin - 1024 || ss > h->smem_optin) {
         g_create_error = "problem too large for shared memory (builder " + std::to_string(sb) + " B, sim " +
                          std::to_string(ss) + " B)";
         mpcgpu_destroy(h);
         return MPCGPU_ERR_UNSUPPORTED;
     }
-    if (t.L.has_ov_bounds) {
-        g_create_error = "finite OV bounds (soft output constraints) are not supported by this build";
-        mpcgpu_destroy(h);
-        return MPCGPU_ERR_UNSUPPORTED;
+    if (t.L.has_ov_bounds) {   // soft output constraints run on the block-per-run kernel (mpc_soft.cuh)
+        const size_t sf = soft_smem_doubles(t.L, t.L.nu, sim_pad(t.L.mmax)) * sizeof(double);
+        if (sf > h->smem_optin || t.L.nst > SOFT_THREADS || !(t.L.rho_ecr > 0.0)) {
+            g_create_error = "soft output constraints: problem too large for the block kernel (shared memory " +
+                             std::to_string(sf) + " B, nst " + std::to_string(t.L.nst) + ") or Weights.ECR <= 0";
+            mpcgpu_destroy(h);
+            return MPCGPU_ERR_UNSUPPORTED;
+        }
     }
     *out = h;
     return MPCGPU_OK;
@@ -248,7 +270,7 @@ extern "C" void mpcgpu_destroy(mpcgpu_handle *h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    h->dTG.release(); h->dTK.release(); h->dS1.release(); h->dR.release(); h->dV.release(); h->dYref.release();
+    h->dTG.release(); h->dTK.release(); h->dS1.release(); h->dST.release(); h->dPA.release(); h->dR.release(); h->dV.release(); h->dYref.release();
     h->dN.release(); h->dNu.release(); h->dOrder.release(); h->dInvalid.release(); h->dBStatus.release();
     h->dStatus.release(); h->dOffM.release(); h->dOffW.release(); h->dDelta.release(); h->dLambda.release();
     h->dM.release(); h->dW.release(); h->dCost.release(); h->dPart.release(); h->dY.release(); h->dU.release();
@@ -409,6 +431,7 @@ extern "C" int mpcgpu_run(mpcgpu_handle *h, int cost_mode, int want_traj, void *
         const auto &bk = h->buckets[b];
         const size_t smem = mpc_builder_smem_doubles(nu * bk.mmax, L.nst) * sizeof(double);
         k_build<<<bk.count, BUILD_THREADS, smem, h->pool[b % NSTREAM]>>>(L, T, h->dOrder.p + bk.off, bk.count, C);
+        CK(cudaGetLastError());
         launches++;
     }
     for (int i = 0; i < nfork; ++i) {
@@ -422,10 +445,17 @@ extern "C" int mpcgpu_run(mpcgpu_handle *h, int cost_mode, int want_traj, void *
     long long item0 = 0;
     for (int b = 0; b < nb; ++b) {
         const auto &bk = h->buckets[b];
-        const size_t smem = sim_smem_doubles(L, nu, bk.P) * sizeof(double);
         const int grid = bk.count * runs;
-        sim_kernel(nu, bk.P)<<<grid, 32, smem, h->pool[b % NSTREAM]>>>(L, T, h->dOrder.p + bk.off, bk.count, runs, cost_mode,
-                                                                       square, item0, C, O);
+        if (L.has_ov_bounds) {
+            const size_t smem = soft_smem_doubles(L, nu, bk.P) * sizeof(double);
+            soft_kernel(nu, bk.P)<<<grid, SOFT_THREADS, smem, h->pool[b % NSTREAM]>>>(L, T, h->dOrder.p + bk.off, bk.count, runs,
+                                                                                   cost_mode, square, item0, C, O);
+        } else {
+            const size_t smem = sim_smem_doubles(L, nu, bk.P) * sizeof(double);
+            sim_kernel(nu, bk.P)<<<grid, 32, smem, h->pool[b % NSTREAM]>>>(L, T, h->dOrder.p + bk.off, bk.count, runs, cost_mode,
+                                                                           square, item0, C, O);
+        }
+        CK(cudaGetLastError());
         item0 += grid;
         launches++;
     }

@@ -6,6 +6,9 @@
 #define MPC_HOST_EMULATION 1
 #include "simt.h"
 int g_sim_knob = 0;
+double *g_soft_dump = nullptr;
+int g_soft_dump_k = -1, g_soft_k = -2;
+extern "C" void emu_soft_dump(double *p, int k) { g_soft_dump = p; g_soft_dump_k = k; }
 int g_sim_verbose = 0;
 extern "C" void emu_set_verbose(int v) { g_sim_verbose = v; }
 long long g_sim_reappends = 0, g_sim_rotations = 0;
@@ -21,6 +24,7 @@ extern "C" long long emu_reappends() { long long r = g_sim_reappends; g_sim_reap
 
 #include "../../model-predictive-control-tuning_b200/csrc/mpc_core.cuh"
 #include "../../model-predictive-control-tuning_b200/csrc/mpc_sim.cuh"
+#include "../../model-predictive-control-tuning_b200/csrc/mpc_soft.cuh"
 #include "../../model-predictive-control-tuning_b200/csrc/mpc_tables.h"
 
 template <int NU>
@@ -40,6 +44,35 @@ static int sim_dispatch(int nu, int P, const MpcLayout &L, const MpcTables &T, i
         case 3: return sim_p<3>(P, L, T, m, Mg, Wg, mode, sel, smem, gscr, out);
         default: return sim_p<4>(P, L, T, m, Mg, Wg, mode, sel, smem, gscr, out);
     }
+}
+
+template <int NU>
+static int soft_p(int P, const MpcLayout &L, const MpcTables &T, int p, int m, const double *Mg, const double *Wg, int mode, int sel,
+                  double *smem, const MpcRunOut &out) {
+    switch (P) {
+        case 4: return soft_run<NU, 4>(L, T, p, m, Mg, Wg, mode, sel, smem, out);
+        case 8: return soft_run<NU, 8>(L, T, p, m, Mg, Wg, mode, sel, smem, out);
+        default: return soft_run<NU, 16>(L, T, p, m, Mg, Wg, mode, sel, smem, out);
+    }
+}
+// one CTA = SOFT_THREADS host threads (plants with soft output constraints)
+static int run_block(int nu, int P, const MpcLayout &L, const MpcTables &T, int p, int m, const double *Mg, const double *Wg,
+                     int mode, int sel, const MpcRunOut &out) {
+    std::vector<double> smem(soft_smem_doubles(L, nu, P) + 8, std::nan(""));
+    int status[SOFT_THREADS];
+    simt_run_block([&]() {
+        int st;
+        switch (nu) {
+            case 1: st = soft_p<1>(P, L, T, p, m, Mg, Wg, mode, sel, smem.data(), out); break;
+            case 2: st = soft_p<2>(P, L, T, p, m, Mg, Wg, mode, sel, smem.data(), out); break;
+            case 3: st = soft_p<3>(P, L, T, p, m, Mg, Wg, mode, sel, smem.data(), out); break;
+            default: st = soft_p<4>(P, L, T, p, m, Mg, Wg, mode, sel, smem.data(), out); break;
+        }
+        status[threadIdx.x] = st;
+    }, SOFT_THREADS);
+    for (int l = 1; l < SOFT_THREADS; ++l)
+        if (status[l] != status[0]) return 99;
+    return status[0];
 }
 
 // one warp = 32 host threads
@@ -66,7 +99,8 @@ extern "C" int emu_eval_batch(const mpcgpu_problem *pb, int n, const int *N, con
     std::string e = mpc_build_tables(*pb, ht);
     if (!e.empty()) { std::strncpy(err, e.c_str(), errlen - 1); return 1; }
     const MpcLayout &L = ht.L;
-    MpcTables T{ht.TG.data(), ht.TK.data(), ht.S1.data(), ht.r.data(), ht.v.data(), ht.yref.data()};
+    MpcTables T{ht.TG.data(), ht.TK.data(), ht.S1.data(), ht.r.data(), ht.v.data(), ht.yref.data(),
+                ht.step.data(), ht.pa.data(), L.pmax + L.mmax + 2};
     const int ny = L.ny, nu = L.nu, nit = L.nit;
     const bool square = ny == nu;
     for (int c = 0; c < n; ++c) {
@@ -92,7 +126,8 @@ extern "C" int emu_eval_batch(const mpcgpu_problem *pb, int n, const int *N, con
                     MpcRunOut out{part, y ? y + (size_t)c * ny * nit : nullptr, u ? u + (size_t)c * nu * nit : nullptr,
                                   ys ? ys + (size_t)c * ny * nit : nullptr, uopt ? uopt + (size_t)c * nu * nit : nullptr,
                                   counters, nullptr, nullptr};
-                    int s2 = run_warp(nu, P, L, T, m, Mg.data(), Wg.data(), 2, square ? rn : -1, out);
+                    int s2 = L.has_ov_bounds ? run_block(nu, P, L, T, p, m, Mg.data(), Wg.data(), 2, square ? rn : -1, out)
+                                             : run_warp(nu, P, L, T, m, Mg.data(), Wg.data(), 2, square ? rn : -1, out);
                     if (s2) st = s2;
                     F += part[0];
                 }
@@ -101,7 +136,8 @@ extern "C" int emu_eval_batch(const mpcgpu_problem *pb, int n, const int *N, con
                 MpcRunOut out{mode == 1 ? cost + (size_t)c * ny : nullptr, y ? y + (size_t)c * ny * nit : nullptr,
                               u ? u + (size_t)c * nu * nit : nullptr, ys ? ys + (size_t)c * ny * nit : nullptr,
                               uopt ? uopt + (size_t)c * nu * nit : nullptr, counters, nullptr, g_trace};
-                st = run_warp(nu, P, L, T, m, Mg.data(), Wg.data(), mode, -2, out);
+                st = L.has_ov_bounds ? run_block(nu, P, L, T, p, m, Mg.data(), Wg.data(), mode, -2, out)
+                                     : run_warp(nu, P, L, T, m, Mg.data(), Wg.data(), mode, -2, out);
             }
         } else if (cost) {
             if (mode == 1) for (int i = 0; i < ny; ++i) cost[(size_t)c * ny + i] = NAN;

@@ -25,8 +25,11 @@ struct SimtWarp {
     long long xi[32];
     unsigned vote[32];
 };
-static thread_local SimtDim3 threadIdx, blockIdx;
+static thread_local SimtDim3 threadIdx, blockIdx, blockDim;
 static thread_local SimtWarp *simt_warp = nullptr;
+static thread_local std::barrier<> *simt_block = nullptr;
+static inline void __syncthreads() { simt_block->arrive_and_wait(); }
+static inline long long clock64() { return 0; }
 
 static inline void __syncwarp(unsigned = 0xffffffffu) { simt_warp->bar.arrive_and_wait(); }
 
@@ -93,6 +96,21 @@ static inline void simt_run_warp(const std::function<void()> &fn, unsigned block
             threadIdx.x = l;
             blockIdx.x = block;
             simt_warp = &w;
+            fn();
+        });
+    for (auto &t : th) t.join();
+}
+
+// run fn() as one CTA of `nthreads` threads (block-level code: __syncthreads only, no warp intrinsics)
+static inline void simt_run_block(const std::function<void()> &fn, unsigned nthreads) {
+    std::barrier<> bar((std::ptrdiff_t)nthreads);
+    std::vector<std::thread> th;
+    for (unsigned l = 0; l < nthreads; ++l)
+        th.emplace_back([&, l]() {
+            threadIdx.x = l;
+            blockDim.x = nthreads;
+            blockIdx.x = 0;
+            simt_block = &bar;
             fn();
         });
     for (auto &t : th) t.join();

@@ -61,3 +61,23 @@ def test_invalid_horizons_are_flagged():
     N = np.array([5, 300, 10, 20], dtype=np.int32); Nu = np.array([5, 3, 0, 4], dtype=np.int32)
     g, st, _, _ = emu.eval_batch(p, N, Nu, np.ones((4, 3)), np.ones((4, 3)), "gam")
     assert list(st) == [4, 4, 4, 0]
+
+
+def test_soft_output_constraints_block_kernel():
+    """csrc/mpc_soft.cuh (one CTA per run, square-root dual active set) on a shortened Shell7x5: the measured
+    disturbance enters at k = 19 and pushes the band-controlled outputs into their soft limits."""
+    from mpcgpu import shell7x5
+    p = short(shell7x5(), 27)   # 128 host threads and a barrier per phase: keep it short
+    op = orc.OracleProblem(p)
+    N = np.array([12], dtype=np.int32); Nu = np.array([3], dtype=np.int32)
+    dl = np.zeros((1, 7)); lm = np.array([[0.06, 0.02, 1.6]])
+    g0, st0, stats = orc.eval_batch(op, N, Nu, dl, lm, "gam")
+    g1, st1, cnt, tr = emu.eval_batch(p, N, Nu, dl, lm, "gam", traj=True)
+    assert (st0 == 0).all() and (st1 == 0).all(), (st0, st1)
+    assert int(cnt[0]) > 0 and int(cnt[1]) > 0
+    rel = np.abs(g1 - g0) / np.abs(g0)
+    assert rel.max() < 1e-6, rel
+    for c in range(1):
+        y, u, ys, uo, rc, _ = orc.closedloop(op, N[c], Nu[c], dl[c], lm[c])
+        for a, b in zip(tr, (y, u, ys, uo)):
+            assert np.abs(a[c] - b).max() < TOL_TRAJ
