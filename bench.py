@@ -89,11 +89,22 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(self.samples)}
 
 
+def host_threads():
+    """All host threads this process may use.  torchrun exports OMP_NUM_THREADS=1, which would silently make the
+    reference arm single-threaded, so the count is taken from the affinity mask and passed to the oracle explicitly."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_reference_rate(prob, N, Nu, delta, lam, mode, budget_s=12.0, nthreads=0):
     """Times the CPU oracle (the port of the reference's path) on a bounded sample of the same population."""
     from oracle import oracle as orc
     op = orc.OracleProblem(prob)
-    cores = orc.num_threads() if nthreads <= 0 else nthreads
+    if nthreads <= 0:
+        nthreads = host_threads()
+    cores = nthreads
     probe = min(len(N), max(2 * cores, 16))
     t0 = time.perf_counter()
     orc.eval_batch(op, N[:probe], Nu[:probe], delta[:probe], lam[:probe], mode, nthreads)
@@ -116,18 +127,18 @@ def run_reference(args):
     N, Nu, delta, lam = mpcgpu.synthetic_population(prob, args.pop, seed=0)
     from oracle import oracle as orc
     op = orc.OracleProblem(prob)
-    cores = orc.num_threads()
+    cores = host_threads()
     # bounded sample per step: ~ (2.5 s * cores) of CPU work
     t0 = time.perf_counter()
     probe = min(args.pop, max(2 * cores, 16))
-    orc.eval_batch(op, N[:probe], Nu[:probe], delta[:probe], lam[:probe], args.mode)
+    orc.eval_batch(op, N[:probe], Nu[:probe], delta[:probe], lam[:probe], args.mode, cores)
     dt = time.perf_counter() - t0
     n = int(min(args.pop, max(probe, probe * 2.5 / max(dt, 1e-3))))
     for _ in range(args.warmup):
-        orc.eval_batch(op, N[:n], Nu[:n], delta[:n], lam[:n], args.mode)
+        orc.eval_batch(op, N[:n], Nu[:n], delta[:n], lam[:n], args.mode, cores)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        orc.eval_batch(op, N[:n], Nu[:n], delta[:n], lam[:n], args.mode)
+        orc.eval_batch(op, N[:n], Nu[:n], delta[:n], lam[:n], args.mode, cores)
     dt = time.perf_counter() - t0
     val = n * args.steps / dt
     sample = f"first {n} of the {args.pop}-candidate seeded Shell3x3 population per step"

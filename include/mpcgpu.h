@@ -41,7 +41,8 @@ enum {
     MPCGPU_CAND_INFEASIBLE = 1,   /* QP infeasible (cannot happen with MV box + rate limits only) */
     MPCGPU_CAND_ITER_CAP = 2,     /* active-set iteration cap hit                                 */
     MPCGPU_CAND_NOT_PD = 3,       /* Hessian not positive definite (lambda == 0 and rank-deficient G) */
-    MPCGPU_CAND_INVALID = 4       /* horizons illegal: PreCon.m:23 / VNS2.m:135 (only if check_valid) */
+    MPCGPU_CAND_INVALID = 4,      /* horizons illegal: PreCon.m:23 / VNS2.m:135 (only if check_valid) */
+    MPCGPU_CAND_BOUND_CROSSED = 5 /* NMPC only: a state/OV bound (soft in the Toolbox, not enforced here) was crossed; cost is still returned */
 };
 
 /* cost modes */
@@ -167,6 +168,42 @@ const char *mpcgpu_dtc_last_error(mpcgpu_dtc_handle *h);
  * {step_len, pmax, MAXNA, MAXCP, sum duM, sum(na+1)}, [8+i] na_i, [16+i] dmin_i, [24+i*nu+j] cp_ij, [48+j] duM_j;
  * step: ny*nu*step_len, ftab: ny*(pmax+1)*MAXNA, ug: ny*nu*(pmax+1)*MAXCP.  Any output may be NULL. */
 int mpcgpu_dtc_host_tables(const mpcgpu_dtc_problem *problem, int32_t *info, double *step, double *ftab, double *ug);
+
+
+/* ------------------------------------------------------------------------------------------------
+ * Nonlinear path (BASELINE.json configs[4]): batched
+ *   [y,u,yopt,uopt] = closedloop_toolbox_nmpc(nmpcobj,model,init,r,N,Nu,delta,lambda,nit)
+ *        /root/reference/MPC-Tuning/MPC_Tuning/closedloop_toolbox_nmpc.m:1
+ * with the GAM / VNS objectives fused (GAM_fun.m:87,110-115; VNS2.m:147-195 nonlinear branch) for the plant of
+ *   /root/reference/MPC-Tuning/vandevusse_model.m:39-77 (3 states, 2 MVs, outputs = states 2..3, :73).
+ * The controller call nlmpcmove is restated as: MV levels over the control horizon as decision variables, cost
+ * sum (delta/sy (r - y))^2 + sum (lambda/su du)^2 with r held over the horizon, hard MV bounds, prediction = plant =
+ * RK4 with `nsub` sub-steps per sample; solved by Gauss-Newton SQP with an exact box-QP step.
+ * ---------------------------------------------------------------------------------------------- */
+enum { MPCGPU_MODEL_VANDEVUSSE = 0 };
+typedef struct {
+    int32_t nit, pmax, mmax;     /* samples; 2^nbp - 1; 2^nbc - 1 (<= 15)                                  */
+    int32_t inK;                 /* 1-based first cost sample of the VNS objective (VNS2.m:43: 10)          */
+    int32_t nsub, max_sqp;       /* RK4 sub-steps per sample (>= 4 for this plant); SQP iteration cap       */
+    int32_t model, reserved;     /* MPCGPU_MODEL_VANDEVUSSE                                                 */
+    double Ts;
+    const double *x0, *u0;       /* init.x0 (3), init.u0 (2)                                                */
+    const double *umin, *umax;   /* MV(i).Min / Max (2)                                                     */
+    const double *xmin, *xmax;   /* States(i).Min / Max (3): checked, not enforced (may be NULL)            */
+    const double *su, *sy;       /* MV / OV ScaleFactor (2, 2)                                              */
+    const double *r, *yref;      /* 2 x nit set-point and reference trajectory, signals x time              */
+} mpcgpu_nmpc_problem;
+typedef struct mpcgpu_nmpc_handle mpcgpu_nmpc_handle;
+int mpcgpu_nmpc_create(const mpcgpu_nmpc_problem *problem, int device, mpcgpu_nmpc_handle **out);
+void mpcgpu_nmpc_destroy(mpcgpu_nmpc_handle *h);
+/* N, Nu: n; delta, lambda: n x 2 row-major; cost_mode RAW | GAM (cost n x 2) | VNS (cost n);
+ * r_override: NULL or 2 x nit set-point for this call (closedloop_toolbox_nmpc takes r per call);
+ * y, u, yopt, uopt: NULL or n x 2 x nit; status: NULL or n. */
+int mpcgpu_nmpc_eval_batch(mpcgpu_nmpc_handle *h, int n, const int32_t *N, const int32_t *Nu, const double *delta,
+                           const double *lambda, int cost_mode, const double *r_override, double *cost, double *y, double *u,
+                           double *yopt, double *uopt, int32_t *status);
+int mpcgpu_nmpc_get_counters(mpcgpu_nmpc_handle *h, mpcgpu_counters *out); /* qp_solves = controller calls, as_iterations = SQP iterations */
+const char *mpcgpu_nmpc_last_error(mpcgpu_nmpc_handle *h);
 
 #ifdef __cplusplus
 }

@@ -92,6 +92,13 @@ def load_library():
     lib.mpcgpu_dtc_destroy.restype = None
     lib.mpcgpu_dtc_eval_batch.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 11
     lib.mpcgpu_dtc_host_tables.argtypes = [C.c_void_p] * 5
+    lib.mpcgpu_nmpc_last_error.restype = C.c_char_p
+    lib.mpcgpu_nmpc_last_error.argtypes = [C.c_void_p]
+    lib.mpcgpu_nmpc_create.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
+    lib.mpcgpu_nmpc_destroy.argtypes = [C.c_void_p]
+    lib.mpcgpu_nmpc_destroy.restype = None
+    lib.mpcgpu_nmpc_eval_batch.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 7
+    lib.mpcgpu_nmpc_get_counters.argtypes = [C.c_void_p, C.POINTER(Counters)]
     _lib = lib
     return lib
 
@@ -102,4 +109,5 @@ EXPORTED_SYMBOLS = [
     "mpcgpu_measure_fp64_peak",
     "mpcgpu_dtc_create", "mpcgpu_dtc_destroy", "mpcgpu_dtc_eval_batch", "mpcgpu_dtc_last_error",
     "mpcgpu_dtc_host_tables",
+    "mpcgpu_nmpc_create", "mpcgpu_nmpc_destroy", "mpcgpu_nmpc_eval_batch", "mpcgpu_nmpc_get_counters", "mpcgpu_nmpc_last_error",
 ]
