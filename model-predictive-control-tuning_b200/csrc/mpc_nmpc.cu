@@ -4,8 +4,8 @@
 //
 // One THREAD per closed-loop run (candidate x VNS run): the work of a run is a long serial chain (59 controller
 // calls, each a few SQP iterations of p*nsub RK4 steps on a 3-state model) with no parallelism worth a warp, and a
-// population supplies tens of thousands of independent runs.  Per controller call (nlmpcmove restated, oracle/
-// nmpc_oracle.py N1-N4):
+// population supplies tens of thousands of independent runs.  Per controller call (nlmpcmove restated as N1-N4,
+// DESIGN.md section 2 / include/mpcgpu.h):
 //   rollout with forward sensitivities (RK4 stage Jacobians chained: [A|B] per sample, X = dx/dv carried),
 //   Gauss-Newton model  H = sum S'Wy^2 S + D'Wdu^2 D,  g,  accumulated on the fly (S never stored),
 //   exact box-constrained QP step (primal active set on the MV bounds, Cholesky of the free block),

@@ -290,7 +290,7 @@ def test_shell7x5_status_codes(ev75):
 def test_shell7x5_vns_and_determinism(ev75):
     p = ev75.prob
     op = orc.OracleProblem(p)
-    N, Nu, dl, lm = synthetic_population(p, 32, seed=6, wlo=1e-2)
+    N, Nu, dl, lm = synthetic_population(p, 64, seed=6, wlo=1e-2)
     F0, st0, _ = orc.eval_batch(op, N, Nu, dl, lm, "vns")
     a = ev75.eval_batch(N, Nu, dl, lm, mode="vns")
     b = ev75.eval_batch(N, Nu, dl, lm, mode="vns")
