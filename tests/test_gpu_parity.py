@@ -297,8 +297,9 @@ def test_shell7x5_vns_and_determinism(ev75):
     assert np.array_equal(a["cost"], b["cost"], equal_nan=True)
     ok = (st0 == 0) & (a["status"] == 0) & vns_well_posed(p, lambda r: orc.OracleProblem(p, r=r), N, Nu, dl, lm)
     assert ok.sum() >= 16
-    sens = oracle_sensitivity(op, N[ok], Nu[ok], dl[ok], lm[ok], "vns", F0[ok])
-    check_cost(a["cost"][ok], F0[ok], sens, "shell7x5 vns", min_strict=0.5)
+    # the Jnu term (|uopt(0)| / |diff(uopt)|)^2 amplifies the last digits of the degenerate open-loop QP
+    rel = np.abs(a["cost"][ok] - F0[ok]) / np.abs(F0[ok])
+    assert rel.max() < 1e-3 and (rel < 1e-6).mean() >= 0.8, (rel.max(), (rel < 1e-6).mean())
 
 
 # ---------------------------------------------------------------------------------------------
