@@ -362,3 +362,18 @@ def test_nmpc_population_properties():
         g0, st0 = no.gam_cost(prob, N[i], Nu[i], dl[i], lm[i])
         assert (np.abs(a["cost"][i] - g0) / np.abs(g0)).max() < 1e-4, (i, a["cost"][i], g0)
     ev.close()
+
+
+def test_batched_tuner_on_shell3x3(ev3):
+    """the hybrid tuner driven in populations (mpcgpu/tuner.py).  Starting from the reference's
+    start point (N = 127, Nu = 2, delta = lambda = 1, MPCTuning.m:283-302) it must end at a legal tuning whose GAM
+    cost beats the start by a wide margin, within a few hundred thousand closed-loop evaluations."""
+    from mpcgpu import tuner
+    p = ev3.prob
+    lines = []
+    out = tuner.tune_linear(ev3, w=[0.05, 0.40, 0.55], log=lines.append, pop=256, iters=8, max_outer=3)   # w: Shell3x3.m:161
+    assert p.valid(int(out["N"]), int(out["Nu"].max()))
+    g0 = ev3.eval_batch([127], [2], np.ones((1, 3)), np.ones((1, 3)), mode="gam")["cost"][0]
+    g1 = ev3.eval_batch([out["N"]], [int(out["Nu"].max())], out["delta"][None], out["lam"][None], mode="gam")["cost"][0]
+    assert g1.sum() < 0.2 * g0.sum(), (g0, g1, out)
+    assert out["evaluations"] > 2000 and any(l.startswith("Fvns=") for l in lines)
