@@ -101,14 +101,21 @@ __device__ __forceinline__ double sim_wmax(double v) {
     for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(SIM_FULL, v, o));
     return v;
 }
-// all lanes end with the minimum value and, among equal values, the smallest non-negative index
+// all lanes end with the minimum value and, among equal values, the smallest non-negative index.
+// Three warp-wide integer reductions (redux.sync) on an order-preserving 64-bit key instead of a five-step shuffle
+// butterfly on (double, int) pairs: this was the single hottest line of the active-set path (profiles/r1f).
 __device__ __forceinline__ void sim_wargmin(double &v, int &i) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const double ov = __shfl_xor_sync(SIM_FULL, v, o);
-        const int oi = __shfl_xor_sync(SIM_FULL, i, o);
-        if (ov < v || (ov == v && oi >= 0 && (i < 0 || oi < i))) { v = ov; i = oi; }
-    }
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    const unsigned long long key = (b >> 63) ? ~b : (b | 0x8000000000000000ull);   // unsigned order == numeric order
+    const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
+    const unsigned mhi = __reduce_min_sync(SIM_FULL, hi);
+    const unsigned mlo = __reduce_min_sync(SIM_FULL, hi == mhi ? lo : 0xffffffffu);
+    const bool mine = hi == mhi && lo == mlo;
+    const unsigned mi = __reduce_min_sync(SIM_FULL, (mine && i >= 0) ? (unsigned)i : 0xffffffffu);
+    const unsigned long long mk = ((unsigned long long)mhi << 32) | mlo;
+    const unsigned long long mb = (mk >> 63) ? (mk & 0x7fffffffffffffffull) : ~mk;
+    v = __longlong_as_double((long long)mb);
+    i = mi == 0xffffffffu ? -1 : (int)mi;
 }
 
 template <int NU>
