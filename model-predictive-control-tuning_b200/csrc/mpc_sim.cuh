@@ -487,19 +487,16 @@ struct SimWarp {
                     if (sl[type] < bv || (sl[type] == bv && bi >= 0 && id < bi)) { bv = sl[type]; bi = id; }
                 }
             }
-#ifndef SIM_PIVOT_MOST_VIOLATED
-            if (!SIM_KNOB(2)) {   // pivot rule: among the violated constraints take the EARLIEST horizon index first (then the
-                // most violated).  Any violated constraint is a valid Goldfarb-Idnani pivot; walking the
-                // horizon in time order follows how rate/level saturation propagates and avoids most of the
-                // add/drop churn of the most-violated rule (measured: 233 -> see DESIGN.md).
-                double ckey = bi >= 0 ? (double)(row[0] & (P - 1)) : 1e9;
-                int dummy = bi >= 0 ? 0 : -1;
-                sim_wargmin(ckey, dummy);
-                if (bi >= 0 && (double)(row[0] & (P - 1)) != ckey) { bv = -SIM_VIOL_TOL; bi = -1; }
+            {   // pivot rule: among the violated constraints take the EARLIEST horizon index first (then the most
+                // violated).  Any violated constraint is a valid Goldfarb-Idnani pivot; walking the horizon in time
+                // order follows how rate/level saturation propagates and avoids most of the add/drop churn of the
+                // most-violated rule.  One integer warp reduction finds that index -- and tells when nothing is violated.
+                const unsigned cmine = bi >= 0 ? (unsigned)(row[0] & (P - 1)) : 0xffffu;
+                const unsigned cmin = __reduce_min_sync(SIM_FULL, cmine);
+                if (cmin == 0xffffu) break;
+                if (!SIM_KNOB(2) && cmine != cmin) { bv = -SIM_VIOL_TOL; bi = -1; }
             }
-#endif
             sim_wargmin(bv, bi);
-            if (bi < 0) break;
             const int p = bi;
             SIM_DBG("  pivot %c%d.%d viol %.3e (q=%d)\n", "dDuU"[p & 3], (p >> 2) / P, (p >> 2) % P, bv, q);
             double sp = bv, mu_p = 0.0;
@@ -549,8 +546,9 @@ struct SimWarp {
                 drop_flagged();
             }
         }
-        // ---- one Newton correction on the active constraints if they drifted: z += V Li (-slack_A) ----
-        if (q > 0) {
+        // ---- one Newton correction on the active constraints if they drifted: z += V Li (-slack_A).  Only after
+        // the set changed in this solve: an unchanged set was corrected (or found clean) with these factors before ----
+        if (q > 0 && it > 0) {
             publish(lv);
             double worst = 0.0;
             for (int a = lane; a < q; a += 32) {
@@ -584,7 +582,8 @@ struct SimWarp {
             int sg = 0;
 #pragma unroll 2
             for (; sg + 1 < nst; sg += 2) {
-                const double s0 = sm.st[sg], s1 = sm.st[sg + 1];
+                const double2 s01 = *reinterpret_cast<const double2 *>(sm.st + sg);   // st is 16-byte aligned
+                const double s0 = s01.x, s1 = s01.y;
 #pragma unroll
                 for (int s = 0; s < NSLOT; ++s)
                     if (row[s] < R) {

@@ -33,7 +33,7 @@ struct DevOut {
 template <int NU, int P>
 __global__ void __launch_bounds__(32) k_sim(const MpcLayout L, const MpcTables T, const int *order, int count, int runs,
                                             int mode, int square, long long item0, DevCand C, DevOut O) {
-    extern __shared__ double smem_s[];
+    extern __shared__ __align__(16) double smem_s[];
     const int item = blockIdx.x;
     if (item >= count * runs) return;
     const int c = order[item / runs];

@@ -163,8 +163,15 @@ class DtcEvaluator:
         delta = np.ascontiguousarray(delta, dtype=np.float64).reshape(n, self.ny)
         lam = np.ascontiguousarray(lam, dtype=np.float64).reshape(n, self.nu)
         if filters is None:
+            # the design depends on (alfa, raio) only through which poles count as slow: design once per distinct pair
             alfa = np.broadcast_to(np.asarray(alfa, float), (n,)); raio = np.broadcast_to(np.asarray(raio, float), (n,))
-            filters = [mimo_filter(self.prob.pnz, float(a), float(rr)) for a, rr in zip(alfa, raio)]
+            cache = {}
+            filters = []
+            for a, rr in zip(alfa.tolist(), raio.tolist()):
+                key = (a, rr)
+                if key not in cache:
+                    cache[key] = mimo_filter(self.prob.pnz, a, rr)
+                filters.append(cache[key])
         num, den, ln = self.pack_filters(filters)
         ise = np.empty((n, self.ny)); status = np.zeros(n, dtype=np.int32)
         y = np.empty((n, self.ny, self.nit)) if traj else None

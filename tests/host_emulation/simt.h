@@ -18,6 +18,7 @@
 #define __restrict__
 #define MPC_SIMT_EMULATION 1
 
+struct double2 { double x, y; };
 struct SimtDim3 { unsigned x = 0, y = 0, z = 0; };
 struct SimtWarp {
     std::barrier<> bar{32};
