@@ -531,10 +531,7 @@ struct SimWarp {
                     for (int s = 0; s < NSLOT; ++s) z[s] += t * dir[s];
                     sp += t * rho;
                 }
-                for (int a = lane; a < q; a += 32) {
-                    sm.mu[a] -= t * sm.rr[a];
-                    sm.dflag[a] = (a == l1) && !full;
-                }
+                for (int a = lane; a < q; a += 32) sm.mu[a] -= t * sm.rr[a];
                 mu_p += t;
                 __syncwarp();
                 if (!full) SIM_DBG("    partial step t=%.3e drop pos %d (%c%d.%d) dependent=%d\n", t, l1, "dDuU"[sm.act[l1 < 0 ? 0 : l1] & 3], (sm.act[l1 < 0 ? 0 : l1] >> 2) / P, (sm.act[l1 < 0 ? 0 : l1] >> 2) % P, dependent);
@@ -543,7 +540,7 @@ struct SimWarp {
                     q += 1;
                     break;
                 }
-                drop_flagged();
+                remove_at(l1);   // the blocking constraint (its multiplier just reached zero)
             }
         }
         // ---- one Newton correction on the active constraints if they drifted: z += V Li (-slack_A).  Only after
