@@ -60,3 +60,31 @@ def test_mpc_tfob_alternates_until_the_weights_stop_improving():
 
     out = tuner.mpc_tfob(gam_at, vns_at, 1, 1, 127, [2], [1.0], [1.0], [0.5, 0.5], 7, 4, [0], pop=64, iters=15)
     assert out["N"] == 30 and out["Nu"].max() == 4 and abs(np.log(out["delta"][0] / 0.1)) < 0.3
+
+
+def test_tuning_parameters_mat_round_trip(tmp_path, kats):
+    """matio: the struct of MPCTuning.m:374-380 written and read back; the values are the reference's own Shell3x3
+    result (tests/golden/fixture_kats.json, decoded from Shell3x3_Tuning_25Jul2023_12_06.mat)."""
+    from mpcgpu import matio
+    k = kats["Shell3x3_Tuning_25Jul2023_12_06.mat"]
+    f = str(tmp_path / "Shell3x3_Tuning_test.mat")
+    matio.save_tuning(f, k["N"], k["Nu"], k["delta"], k["lambda"], L=k["L"], R=k["R"])
+    back = matio.load_tuning(f)
+    assert back["N"].tolist() == [k["N"]] and back["Nu"].tolist() == k["Nu"]
+    np.testing.assert_array_equal(back["delta"], k["delta"]); np.testing.assert_array_equal(back["lambda"], k["lambda"])
+    np.testing.assert_array_equal(back["L"], k["L"]); np.testing.assert_array_equal(back["Ru"], k["R"][:3])
+
+
+def test_load_tuning_reads_the_reference_files(kats):
+    """Only where the reference tree is mounted (the build container); elsewhere the committed KAT JSON stands in."""
+    import os
+    import pytest
+    from mpcgpu import matio
+    f = "/root/reference/MPC-Tuning/Shell3x3_Tuning_Caso2.mat"
+    if not os.path.exists(f):
+        pytest.skip("reference tree not mounted")
+    got = matio.load_tuning(f)
+    k = kats["Shell3x3_Tuning_Caso2.mat"]
+    assert int(got["N"].max()) == k["N"] and got["Nu"].tolist() == k["Nu"]
+    np.testing.assert_allclose(got["delta"], k["delta"], rtol=0, atol=0)
+    np.testing.assert_allclose(got["L"], k["L"], rtol=0, atol=0)
