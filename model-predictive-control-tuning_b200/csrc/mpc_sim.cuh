@@ -494,7 +494,9 @@ struct SimWarp {
                 const unsigned cmine = bi >= 0 ? (unsigned)(row[0] & (P - 1)) : 0xffffu;
                 const unsigned cmin = __reduce_min_sync(SIM_FULL, cmine);
                 if (cmin == 0xffffu) break;
+#ifndef SIM_PIVOT_MOST_VIOLATED
                 if (!SIM_KNOB(2) && cmine != cmin) { bv = -SIM_VIOL_TOL; bi = -1; }
+#endif
             }
             sim_wargmin(bv, bi);
             const int p = bi;

@@ -3,11 +3,12 @@ sys.path.insert(0,'/root/repo'); sys.path.insert(0,'/root/repo/model-predictive-
 import mpcgpu
 p = mpcgpu.shell3x3(2)
 ev = mpcgpu.Evaluator(p, device=0)
-N, Nu, dl, lm = mpcgpu.synthetic_population(p, 4096, seed=0)
+NPOP = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+N, Nu, dl, lm = mpcgpu.synthetic_population(p, NPOP, seed=0)
 ev.lib.mpcgpu_debug_enable_diag.argtypes=[C.c_void_p, C.c_int]; ev.lib.mpcgpu_debug_get_diag.argtypes=[C.c_void_p, C.c_void_p]
 ev.lib.mpcgpu_debug_enable_diag(ev.h, 1)
 for _ in range(2): out = ev.eval_batch(N, Nu, dl, lm, mode='gam')
-d = np.zeros((4096,4), dtype=np.uint64)
+d = np.zeros((NPOP,4), dtype=np.uint64)
 rc = ev.lib.mpcgpu_debug_get_diag(ev.h, d.ctypes.data_as(C.c_void_p)); print('rc', rc)
 cyc = d[:,3].astype(float); its = d[:,1].astype(float); con = d[:,0].astype(float); qm = d[:,2].astype(float)
 print('cycles: mean %.3g median %.3g p99 %.3g max %.3g (ms at 1.965GHz: max %.2f)'%(cyc.mean(), np.median(cyc), np.percentile(cyc,99), cyc.max(), cyc.max()/1.965e6))
@@ -20,5 +21,5 @@ for P,(lo,hi) in {4:(1,4),8:(5,8),16:(9,15)}.items():
     sel = fast[(Nu[fast]>=lo)&(Nu[fast]<=hi)]
     if len(sel): print('P',P,'fast-only candidates', len(sel), 'cycles/step median %.0f'%(np.median(cyc[sel])/500))
 # regression cycles vs its, con
-A = np.stack([np.ones(4096), con, its, its*qm],1); coef,*_ = np.linalg.lstsq(A, cyc, rcond=None); print('fit cyc ~ %.3g + %.3g*con + %.3g*its + %.3g*its*qmax'%tuple(coef))
+A = np.stack([np.ones(NPOP), con, its, its*qm],1); coef,*_ = np.linalg.lstsq(A, cyc, rcond=None); print('fit cyc ~ %.3g + %.3g*con + %.3g*its + %.3g*its*qmax'%tuple(coef))
 np.save('gpurun_out/diag.npy', d)
