@@ -377,3 +377,57 @@ def test_batched_tuner_on_shell3x3(ev3):
     g1 = ev3.eval_batch([out["N"]], [int(out["Nu"].max())], out["delta"][None], out["lam"][None], mode="gam")["cost"][0]
     assert g1.sum() < 0.2 * g0.sum(), (g0, g1, out)
     assert out["evaluations"] > 2000 and any(l.startswith("Fvns=") for l in lines)
+
+
+# ---------------------------------------------------------------------------------------------
+# Other plant shapes: every template instantiation (nu = 1, 2, 4) of the closed-loop kernels
+# ---------------------------------------------------------------------------------------------
+def _synthetic_problem(ny, nu, nd, nit, seed, soft=False):
+    """A random stable FOPDT plant with hard MV limits (and soft output bands if `soft`), in the shape MPCTuning.m
+    hands to the evaluator; not a reference case -- it exists to run the nu = 1, 2, 4 kernels against the oracle."""
+    from mpcgpu.plant import c2d_fopdt
+    from mpcgpu.problems import LinearProblem
+    rng = np.random.default_rng(seed)
+    nw = nu + nd
+    K = rng.uniform(0.5, 2.0, size=(ny, nw)) * rng.choice([-1.0, 1.0], size=(ny, nw))
+    K[np.arange(min(ny, nu)), np.arange(min(ny, nu))] = np.abs(K[np.arange(min(ny, nu)), np.arange(min(ny, nu))]) + 1.5
+    tau = rng.uniform(5.0, 30.0, size=(ny, nw)); theta = rng.uniform(0.0, 9.0, size=(ny, nw))
+    ch = c2d_fopdt(K, tau, theta, 2.0)
+    r = np.zeros((nit, ny))
+    for i in range(ny):
+        r[10 + 15 * i:, i] = 0.3 * (i + 1) * (-1) ** i
+    v = np.zeros((nit, nd)); v[nit // 2:, :] = 0.4
+    yref = r.T.copy()
+    dmin = ch.d[:, :nu].min(axis=1).astype(np.int32)
+    big = np.inf
+    return LinearProblem(f"synthetic{ny}x{nu}", 2.0, nit, ny, nu, nd, ch, -0.6 * np.ones(nu), 0.8 * np.ones(nu), -0.07 * np.ones(nu),
+                         0.09 * np.ones(nu), (-0.35 * np.ones(ny) if soft else -big * np.ones(ny)), (0.5 * np.ones(ny) if soft else big * np.ones(ny)),
+                         np.ones(ny), np.ones(ny), np.ones(nu), np.ones(ny), 1e3, r, v, yref, dmin, np.zeros(ny, dtype=bool), np.ones(ny), np.ones(nw))
+
+
+@pytest.mark.parametrize("ny,nu,nd,soft", [(1, 1, 0, False), (2, 2, 1, False), (3, 4, 0, False), (4, 4, 1, False), (2, 1, 1, True), (3, 2, 0, True)])
+def test_other_plant_shapes(ny, nu, nd, soft):
+    p = _synthetic_problem(ny, nu, nd, 160, seed=100 + 10 * ny + nu, soft=soft)
+    ev = mpcgpu.Evaluator(p, device=0)
+    op = orc.OracleProblem(p)
+    N, Nu, dl, lm = synthetic_population(p, 40, seed=ny + nu, wlo=1e-2 if soft else 1e-3, whi=3.0)
+    N[0], Nu[0] = 127, 15
+    N[1], Nu[1] = max(int(p.dmin.max()) + 2, 12), 2
+    g0, st0, stats = orc.eval_batch(op, N, Nu, dl, lm, "gam")
+    out = ev.eval_batch(N, Nu, dl, lm, mode="gam", traj=True)
+    ok = (st0 == 0) & (out["status"] == 0)
+    assert ok.sum() >= 36 and stats[2] > 0, (st0, out["status"])
+    sens = oracle_sensitivity(op, N[ok], Nu[ok], dl[ok], lm[ok], "gam", g0[ok])
+    check_cost(out["cost"][ok], g0[ok], sens, p.name, min_strict=0.7)
+    idx = np.where(ok)[0]
+    for c in idx[sens < 1e-8][:10]:
+        y, u, ys, uo, rc, _ = orc.closedloop(op, N[c], Nu[c], dl[c], lm[c])
+        for k, b in zip(("y", "u", "ys", "uopt"), (y, u, ys, uo)):
+            assert np.abs(out[k][c] - b).max() < TOL_TRAJ, (c, k)
+    if p.square and not soft:
+        F0, s0, _ = orc.eval_batch(op, N[:12], Nu[:12], dl[:12], lm[:12], "vns")
+        F = ev.eval_batch(N[:12], Nu[:12], dl[:12], lm[:12], mode="vns")
+        okv = (s0 == 0) & (F["status"] == 0) & vns_well_posed(p, lambda r: orc.OracleProblem(p, r=r), N[:12], Nu[:12], dl[:12], lm[:12])
+        rel = np.abs(F["cost"][okv] - F0[okv]) / np.abs(F0[okv])
+        assert okv.sum() >= 4 and rel.max() < 1e-5, rel
+    ev.close()
