@@ -431,3 +431,20 @@ def test_other_plant_shapes(ny, nu, nd, soft):
         rel = np.abs(F["cost"][okv] - F0[okv]) / np.abs(F0[okv])
         assert okv.sum() >= 4 and rel.max() < 1e-5, rel
     ev.close()
+
+
+def test_nmpc_warp_per_run_variant(monkeypatch):
+    """The alternative lane mapping of the NMPC kernel (MPCGPU_NMPC_WARP_PER_RUN=1) computes the same thing."""
+    from mpcgpu.nmpc import vandevusse, NmpcEvaluator
+    prob = vandevusse()
+    ev = NmpcEvaluator(prob, device=0)
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "oracle_golden_nmpc.npz"))
+    a = ev.eval_batch(gold["N"], gold["Nu"], gold["delta"], gold["lam"], mode="gam", traj=True)
+    monkeypatch.setenv("MPCGPU_NMPC_WARP_PER_RUN", "1")
+    b = ev.eval_batch(gold["N"], gold["Nu"], gold["delta"], gold["lam"], mode="gam", traj=True)
+    assert (b["status"] == 0).all()
+    assert (np.abs(b["y"] - gold["y"]) / prob.sy[None, :, None]).max() < TOL_NMPC_TRAJ
+    assert (np.abs(a["u"] - b["u"]) / prob.su[None, :, None]).max() < 1e-6
+    v = ev.eval_batch(gold["N"][:2], gold["Nu"][:2], gold["delta"][:2], gold["lam"][:2], mode="vns")
+    assert (np.abs(v["cost"] - gold["vns"]) / np.abs(gold["vns"])).max() < 5e-3
+    ev.close()
