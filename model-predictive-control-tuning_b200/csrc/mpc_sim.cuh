@@ -25,6 +25,7 @@
 
 #define SIM_VIOL_TOL 1e-10
 #define SIM_DEP_TOL 1e-13
+#define SIM_CHURN 24   /* iterations per constrained QP above which a run switches its pivot rule */
 #define SIM_REFRESH 96 /* Givens removals after which the active-set factor is rebuilt from W */
 #define SIM_CH 32 /* samples of r / yref / v staged into shared memory at a time */
 #define SIM_INF (__builtin_huge_val())
@@ -150,6 +151,7 @@ struct SimWarp {
     unsigned long long n_con, n_it;
     int qmax;
     int n_rot;      // uniform: Givens removals since the factor was last rebuilt from W
+    int churn;      // uniform: 1 once the run has switched to most-violated-first pivoting (qp_solve)
 
     __device__ __forceinline__ SimWarp(const MpcLayout &L_) : L(L_) {}
 
@@ -425,6 +427,11 @@ struct SimWarp {
         const int itmax = 20 * (NU * m + 10);
         double lv[NSLOT];
         SIM_DBGSET("entry");
+        // Earliest-horizon-first pivoting wins on the population as a whole, but a few very aggressive tunings churn
+        // under it (60-120 add/drop iterations per QP where most-violated-first needs ~35): a run whose running
+        // mean exceeds SIM_CHURN iterations per constrained QP pivots on the most violated constraint instead.
+        if (!churn && n_con > 8 && n_it > (unsigned long long)SIM_CHURN * n_con) churn = 1;   // sticky for the rest of the run
+        const bool most_violated = SIM_KNOB(2) || (!SIM_KNOB(16) && churn);
         if (q > 0 && n_rot > SIM_REFRESH) {   // bound the rounding drift of long rotation sequences
             const int qn = q;
             q = 0;
@@ -495,7 +502,7 @@ struct SimWarp {
                 const unsigned cmin = __reduce_min_sync(SIM_FULL, cmine);
                 if (cmin == 0xffffu) break;
 #ifndef SIM_PIVOT_MOST_VIOLATED
-                if (!SIM_KNOB(2) && cmine != cmin) { bv = -SIM_VIOL_TOL; bi = -1; }
+                if (!most_violated && cmine != cmin) { bv = -SIM_VIOL_TOL; bi = -1; }
 #endif
             }
             sim_wargmin(bv, bi);
@@ -681,7 +688,7 @@ __device__ __forceinline__ int sim_run(const MpcLayout &L, const MpcTables &T, i
         sm.chd = ip; ip += nch; sm.chj = ip; ip += nch; sm.role = ip; ip += nst;
         sm.act = ip; ip += R; sm.dflag = ip; ip += R; sm.misc = ip;
     }
-    wp.gscr = gscr; wp.W = Wg; wp.lane = lane; wp.m = m; wp.q = 0; wp.n_con = 0; wp.n_it = 0; wp.qmax = 0; wp.n_rot = 0;
+    wp.gscr = gscr; wp.W = Wg; wp.lane = lane; wp.m = m; wp.q = 0; wp.n_con = 0; wp.n_it = 0; wp.qmax = 0; wp.n_rot = 0; wp.churn = 0;
 #pragma unroll
     for (int s = 0; s < NSLOT; ++s) {
         const int r = s * 32 + lane;
