@@ -30,7 +30,7 @@
 // ---------------------------------------------------------------------------------------------
 static MPC_HD size_t mpc_builder_smem_doubles(int nz, int nst) { return (size_t)nz * nz + (size_t)(nst + nz) * nz; }
 
-MPC_FN int mpc_build_candidate(const MpcLayout &L, const MpcTables &T, int p, int m, const double *delta,
+MPC_FN int mpc_build_candidate(const MpcLayout &L, const MpcTables &T, int p, int m, int P, const double *delta,
                                const double *lambda, double *smem, double *Mg, double *Wg, int *flag_smem) {
     const int ny = L.ny, nu = L.nu, nw = L.nw, nz = nu * m, ns = L.nst, ncol = ns + nz;
     double *Hs = smem;
@@ -134,7 +134,7 @@ MPC_FN int mpc_build_candidate(const MpcLayout &L, const MpcTables &T, int p, in
     }
     // ---- write out, row-padded input-major: row r = j*P + c, rows with c >= m are zero ----
     {
-        const int P = m <= 4 ? 4 : (m <= 8 ? 8 : 16), R = nu * P;
+        const int R = nu * P;   // P >= m: the padded horizon of the kernel image that will read this candidate
         TFOR(idx, ns * R) {
             const int col = idx / R, r = idx - col * R;
             const int j = r / P, c = r - j * P;

@@ -618,7 +618,7 @@ struct SimWarp {
                 for (int e = 0; e < 8; ++e)
 #pragma unroll
                     for (int s = 0; s < NSLOT; ++s)
-                        mv[e][s] = (s * 32 + lane < R) ? __ldg(mp + (size_t)(sg + e) * R + s * 32) : 0.0;
+                        mv[e][s] = valid[s] ? __ldg(mp + (size_t)(sg + e) * R + s * 32) : 0.0;   // padded rows of M are zero: not fetched
 #pragma unroll
                 for (int e = 0; e < 8; e += 2) {
                     const double s0 = sm.st[sg + e], s1 = sm.st[sg + e + 1];
@@ -630,7 +630,7 @@ struct SimWarp {
                 const double s0 = sm.st[sg];
 #pragma unroll
                 for (int s = 0; s < NSLOT; ++s)
-                    if (s * 32 + lane < R) acc0[s] = fma(__ldg(mp + (size_t)sg * R + s * 32), s0, acc0[s]);
+                    if (valid[s]) acc0[s] = fma(__ldg(mp + (size_t)sg * R + s * 32), s0, acc0[s]);
             }
 #pragma unroll
             for (int s = 0; s < NSLOT; ++s) z[s] = acc0[s] + acc1[s];
@@ -798,58 +798,28 @@ __device__ __forceinline__ int sim_run(const MpcLayout &L, const MpcTables &T, i
         __syncwarp();
     };
 
-    // ---------------- open-loop optimum (closedloop_toolbox.m:85-98) ----------------
-    if (want_ol) {
-        // the fresh controller state: x = 0, histories 0, u(-1) = 0; r = last row, v = last row
-        if (lane < nsig) {
-            const int c = lane;
-            double v;
-            if (c < ny) v = T.r[(size_t)(nit - 1) * ny + c];
-            else if (c < 2 * ny) v = 0.0;
-            else v = T.v[(size_t)(nit - 1) * nd + (c - 2 * ny)];
-            sm.sig[c] = v;
-        }
-        __syncwarp();
-        build_st(sm.sig, nit - 1, false);
-        const int rc = wp.controller_move();
-        if (rc) status = rc;
-        // Uopt rows = SEQUENTIAL cumulative sum of the moves from u(-1) = 0: a move that is exactly 0 must
-        // repeat the previous level bit-for-bit, because VNS2.m:183-191 divides by these differences
-        // (a tree-ordered scan would turn exact zeros into 1-ulp noise and Jnu terms of 1e+30).
-#pragma unroll
-        for (int s = 0; s < NSLOT; ++s)
-            if (wp.row[s] < R) sm.z[wp.row[s]] = wp.z[s];
-        __syncwarp();
-        for (int j = lane; j < NU; j += 32) {
-            double lvl = 0.0;
-            for (int c = 0; c < P; ++c) { lvl += sm.z[j * P + c]; sm.uopt[j * P + c] = lvl; }
-        }
-        __syncwarp();
-        if (mode == 2) {  // Jnu (VNS2.m:183-191)
-            double part = 0.0;
-            for (int j = lane; j < NU; j += 32) {
-                if (sel < 0 || sel == j) {
-                    const double u0 = fabs(sm.uopt[j * P]);
-                    for (int c = 0; c + 1 < m && c + 1 < nit; ++c) {
-                        const double df = fabs(sm.uopt[j * P + c + 1] - sm.uopt[j * P + c]);
-                        const double xn = u0 / df;
-                        if (fabs(xn) <= 1.7976931348623157e308) part += xn * xn;  // inf / nan -> 0 (VNS2.m:186)
-                    }
-                }
+    // ---------------- open-loop optimum (closedloop_toolbox.m:85-98) = pass k = -1, then the closed loop (:50)
+    // with the open-loop rollout (:100) in lock-step.  One loop, so that the controller (and the whole active-set
+    // solver inlined into it) exists ONCE in the kernel image: code size is a first-order cost here, the
+    // instruction cache does not hold the kernel. ----------------
+    for (int k = want_ol ? -1 : 0; k < nit; ++k) {
+        const bool ol = k < 0;
+        if (ol) {
+            // the fresh controller state: x = 0, histories 0, u(-1) = 0; r = last row, v = last row
+            if (lane < nsig) {
+                const int c = lane;
+                double v;
+                if (c < ny) v = T.r[(size_t)(nit - 1) * ny + c];
+                else if (c < 2 * ny) v = 0.0;
+                else v = T.v[(size_t)(nit - 1) * nd + (c - 2 * ny)];
+                sm.sig[c] = v;
             }
-            jnu = sim_wsum(part);
+            __syncwarp();
+        } else if ((k & (SIM_CH - 1)) == 0) {
+            stage_signals(k);
         }
-        // the closed loop starts from an empty active set
-        wp.q = 0;
-#pragma unroll
-        for (int s = 0; s < NSLOT; ++s) wp.amask[s] = 0;
-        __syncwarp();
-    }
-    // ---------------- closed loop (:50) + open-loop rollout (:100) in lock-step ----------------
-    for (int k = 0; k < nit; ++k) {
-        if ((k & (SIM_CH - 1)) == 0) stage_signals(k);
-        const double *sigrow = sm.sig + (size_t)(k & (SIM_CH - 1)) * nsig;
-        build_st(sigrow, k, true);
+        const double *sigrow = ol ? sm.sig : sm.sig + (size_t)(k & (SIM_CH - 1)) * nsig;
+        build_st(sigrow, ol ? nit - 1 : k, !ol);
         const unsigned long long it_before = wp.n_it;
 #ifdef MPC_SIMT_EMULATION
         if (lane == 0) g_sim_verbose = (g_sim_knob >> 16) && k >= (g_sim_knob >> 16) && k < (g_sim_knob >> 16) + 2;
@@ -858,6 +828,40 @@ __device__ __forceinline__ int sim_run(const MpcLayout &L, const MpcTables &T, i
 #endif
         const int rc = wp.controller_move();
         if (rc) status = rc;
+        if (ol) {
+            // Uopt rows = SEQUENTIAL cumulative sum of the moves from u(-1) = 0: a move that is exactly 0 must
+            // repeat the previous level bit-for-bit, because VNS2.m:183-191 divides by these differences
+            // (a tree-ordered scan would turn exact zeros into 1-ulp noise and Jnu terms of 1e+30).
+#pragma unroll
+            for (int s = 0; s < NSLOT; ++s)
+                if (wp.row[s] < R) sm.z[wp.row[s]] = wp.z[s];
+            __syncwarp();
+            for (int j = lane; j < NU; j += 32) {
+                double lvl = 0.0;
+                for (int c = 0; c < P; ++c) { lvl += sm.z[j * P + c]; sm.uopt[j * P + c] = lvl; }
+            }
+            __syncwarp();
+            if (mode == 2) {  // Jnu (VNS2.m:183-191)
+                double part = 0.0;
+                for (int j = lane; j < NU; j += 32) {
+                    if (sel < 0 || sel == j) {
+                        const double u0 = fabs(sm.uopt[j * P]);
+                        for (int c = 0; c + 1 < m && c + 1 < nit; ++c) {
+                            const double df = fabs(sm.uopt[j * P + c + 1] - sm.uopt[j * P + c]);
+                            const double xn = u0 / df;
+                            if (fabs(xn) <= 1.7976931348623157e308) part += xn * xn;  // inf / nan -> 0 (VNS2.m:186)
+                        }
+                    }
+                }
+                jnu = sim_wsum(part);
+            }
+            // the closed loop starts from an empty active set
+            wp.q = 0;
+#pragma unroll
+            for (int s = 0; s < NSLOT; ++s) wp.amask[s] = 0;
+            __syncwarp();
+            continue;
+        }
         if (out.trace && lane == 0) { out.trace[2 * k] = (int)(wp.n_it - it_before); out.trace[2 * k + 1] = wp.q; }
         // apply the first move of every input
 #pragma unroll

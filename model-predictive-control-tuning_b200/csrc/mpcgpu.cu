@@ -39,14 +39,14 @@ static std::string g_create_error;
 
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(BUILD_THREADS) k_build(const MpcLayout L, const MpcTables T, const int *order,
-                                                         int count, DevCand C) {
+                                                         int count, int P, DevCand C) {
     extern __shared__ double smem_b[];
     __shared__ int flag;
     const int item = blockIdx.x;
     if (item >= count) return;
     const int c = order[item];
     const int p = C.N[c], m = C.Nu[c];
-    const int st = mpc_build_candidate(L, T, p, m, C.delta + (size_t)c * L.ny, C.lambda + (size_t)c * L.nu, smem_b,
+    const int st = mpc_build_candidate(L, T, p, m, P, C.delta + (size_t)c * L.ny, C.lambda + (size_t)c * L.nu, smem_b,
                                        C.M + C.offM[c], C.W + C.offW[c], &flag);
     if (threadIdx.x == 0) C.bstatus[c] = st;
 }
@@ -316,7 +316,11 @@ extern "C" int mpcgpu_upload(mpcgpu_handle *h, int n, const int32_t *N, const in
     for (int c = 0; c < n; ++c) {
         const int p = N[c], m = Nu[c];
         if (p < 2 || p > L.pmax || m < 1 || m > L.mmax || m >= p) { h->hInvalid[c] = 1; continue; }
-        const int P = sim_pad(m), b = P == 4 ? 0 : (P == 8 ? 1 : 2);
+        // One kernel image for the whole population (hard-limit plants): three concurrently running instantiations
+        // (P = 4, 8, 16, ~240 KB of SASS each) thrashed the instruction cache -- measured 16.3 ms against 10.8 ms for
+        // 4096 Shell3x3 candidates with everything on the P = 16 image.  MPCGPU_SIZE_BUCKETS=1 restores the buckets.
+        static const bool size_buckets = getenv("MPCGPU_SIZE_BUCKETS") != nullptr;
+        const int P = (size_buckets || L.has_ov_bounds) ? sim_pad(m) : sim_pad(L.mmax), b = P == 4 ? 0 : (P == 8 ? 1 : 2);
         by_p[b].push_back(c);
         if (m > mmax_p[b]) mmax_p[b] = m;
         const long long R = (long long)nu * P;
@@ -431,7 +435,7 @@ extern "C" int mpcgpu_run(mpcgpu_handle *h, int cost_mode, int want_traj, void *
     for (int b = 0; b < nb; ++b) {
         const auto &bk = h->buckets[b];
         const size_t smem = mpc_builder_smem_doubles(nu * bk.mmax, L.nst) * sizeof(double);
-        k_build<<<bk.count, BUILD_THREADS, smem, h->pool[b % NSTREAM]>>>(L, T, h->dOrder.p + bk.off, bk.count, C);
+        k_build<<<bk.count, BUILD_THREADS, smem, h->pool[b % NSTREAM]>>>(L, T, h->dOrder.p + bk.off, bk.count, bk.P, C);
         CK(cudaGetLastError());
         launches++;
     }

@@ -115,7 +115,7 @@ extern "C" int emu_eval_batch(const mpcgpu_problem *pb, int n, const int *N, con
         std::vector<double> bsm(mpc_builder_smem_doubles(nz, L.nst));
         std::vector<double> Mg((size_t)L.nst * R), Wg((size_t)2 * R * R);
         int flag = 0;
-        int st = mpc_build_candidate(L, T, p, m, delta + (size_t)c * ny, lambda + (size_t)c * nu, bsm.data(), Mg.data(),
+        int st = mpc_build_candidate(L, T, p, m, P, delta + (size_t)c * ny, lambda + (size_t)c * nu, bsm.data(), Mg.data(),
                                      Wg.data(), &flag);
         double part[MPC_MAXY + 1];
         if (st == 0) {
