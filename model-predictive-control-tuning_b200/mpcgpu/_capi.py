@@ -7,7 +7,7 @@ import os
 import numpy as np
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_PKG), "csrc", "libmpcgpu.so")
+LIB_PATH = os.environ.get("MPCGPU_LIB") or os.path.join(os.path.dirname(_PKG), "csrc", "libmpcgpu.so")   # MPCGPU_LIB: A/B builds
 
 COST_RAW, COST_GAM, COST_VNS = 0, 1, 2
 _MODES = {"raw": COST_RAW, "gam": COST_GAM, "vns": COST_VNS}
