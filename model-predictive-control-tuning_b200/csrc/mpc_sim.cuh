@@ -235,6 +235,7 @@ struct SimWarp {
             const double *row_a = Lirow(a);
             double a0 = 0.0, a1 = 0.0;
             int b = 0;
+#pragma unroll 1
             for (; b + 1 <= a; b += 2) { a0 = fma(row_a[b], sm.g[b], a0); a1 = fma(row_a[b + 1], sm.g[b + 1], a1); }
             if (b <= a) a0 = fma(row_a[b], sm.g[b], a0);
             const double acc = a0 + a1;
@@ -251,9 +252,11 @@ struct SimWarp {
         for (int a = lane; a < qq; a += 32) {
             double a0 = 0.0, a1 = 0.0;
             int b = a;
+#pragma unroll 1
             for (; b + 1 < qs; b += 2) { a0 = fma(sm.Li[(size_t)b * QC + a], sm.l[b], a0); a1 = fma(sm.Li[(size_t)(b + 1) * QC + a], sm.l[b + 1], a1); }
             if (b < qs) { a0 = fma(sm.Li[(size_t)b * QC + a], sm.l[b], a0); ++b; }
             if (b < QC) b = QC;
+#pragma unroll 1
             for (; b < qq; ++b) a0 = fma(Lirow(b)[a], sm.l[b], a0);   // spilled rows (rare)
             out[a] = a0 + a1;
         }
@@ -277,6 +280,7 @@ struct SimWarp {
             for (int s = 0; s < NSLOT; ++s)
                 if (row[s] < R) acc[s] = fma(ca, sm.V[(size_t)a * R + row[s]], acc[s]);
         }
+#pragma unroll 1
         for (int a = QC; a < qq; ++a) {   // spilled columns (rare)
             const double ca = coef[a];
             const double *va = Vcol(a);
@@ -785,15 +789,18 @@ __device__ __forceinline__ int sim_run(const MpcLayout &L, const MpcTables &T, i
         }
         __syncwarp();
     };
-    auto stage_signals = [&](int k0) {
+    auto stage_signals = [&](int k0) {   // lane = signal column (nsig <= 32), one row per pass: no index division, no unrolling
         const int cnt = (nit - k0) < SIM_CH ? (nit - k0) : SIM_CH;
-        for (int idx = lane; idx < cnt * nsig; idx += 32) {
-            const int kk = idx / nsig, c = idx - kk * nsig;
-            double v;
-            if (c < ny) v = T.r[(size_t)(k0 + kk) * ny + c];
-            else if (c < 2 * ny) v = T.yref[(size_t)(c - ny) * nit + (k0 + kk)];
-            else v = T.v[(size_t)(k0 + kk) * nd + (c - 2 * ny)];
-            sm.sig[kk * nsig + c] = v;
+        const int c = lane;
+#pragma unroll 1
+        for (int kk = 0; kk < cnt; ++kk) {
+            if (c < nsig) {
+                double v;
+                if (c < ny) v = T.r[(size_t)(k0 + kk) * ny + c];
+                else if (c < 2 * ny) v = T.yref[(size_t)(c - ny) * nit + (k0 + kk)];
+                else v = T.v[(size_t)(k0 + kk) * nd + (c - 2 * ny)];
+                sm.sig[kk * nsig + c] = v;
+            }
         }
         __syncwarp();
     };
