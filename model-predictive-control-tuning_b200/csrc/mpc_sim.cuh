@@ -397,32 +397,6 @@ struct SimWarp {
             if (fl) remove_at(a);
         }
     }
-    // Re-append the constraints stored at list positions [from, upto) behind the first `q` (= from on
-    // entry) factor rows, skipping any that has become linearly dependent.  Leaves q = new size.
-    __device__ __forceinline__ void rebuild(int from, int upto) {
-        for (int a = from; a < upto; ++a) {
-            const int cid = sm.act[a];
-            const double mua = sm.mu[a];
-            __syncwarp();
-            double wv[NSLOT];
-            w_times_normal(cid, wv, sm.w2, sm.w2sc);
-            const double gam = ndot(cid, sm.w2, sm.w2sc);
-            const double l2 = schur_vectors(q, sm.w2, sm.w2sc);
-            const double rho = gam - l2;
-#ifdef MPC_SIMT_EMULATION
-            if (lane == 0) g_sim_reappends++;
-#endif
-            if (rho > SIM_DEP_TOL * gam) {
-                add_V(q, sm.l, -1.0, wv);
-                commit(cid, q, rho, mua, wv);
-                q += 1;
-            } else {
-#pragma unroll
-                for (int s = 0; s < NSLOT; ++s)
-                    if (row[s] == (cid >> 2)) amask[s] &= ~(1 << (cid & 3));
-            }
-        }
-    }
     // Dual active-set QP, warm-started from the carried set AS IT IS.  (Shifting the set by one sample to follow the
     // receding horizon was measured to cost more than it saves: the shifted guess sheds most of its members
     // through negative multipliers and has to be rebuilt from W.)  z (registers) in: z_unc, out: optimum.
@@ -436,12 +410,6 @@ struct SimWarp {
         // mean exceeds SIM_CHURN iterations per constrained QP pivots on the most violated constraint instead.
         if (!churn && n_con > 8 && n_it > (unsigned long long)SIM_CHURN * n_con) churn = 1;   // sticky for the rest of the run
         const bool most_violated = SIM_KNOB(2) || (!SIM_KNOB(16) && churn);
-        if (q > 0 && n_rot > SIM_REFRESH) {   // bound the rounding drift of long rotation sequences
-            const int qn = q;
-            q = 0;
-            rebuild(0, qn);
-            n_rot = 0;
-        }
         if (SIM_KNOB(1)) {
             q = 0;
 #pragma unroll
