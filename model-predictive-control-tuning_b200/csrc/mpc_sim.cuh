@@ -27,6 +27,9 @@
 #define SIM_DEP_TOL 1e-13
 #define SIM_CHURN 24   /* iterations per constrained QP above which a run switches its pivot rule */
 #define SIM_REFRESH 96 /* Givens removals after which the active-set factor is rebuilt from W */
+#ifndef SIM_MB
+#define SIM_MB 18 /* columns of M in flight per batch when M is read from global memory (P = 16) */
+#endif
 #define SIM_CH 32 /* samples of r / yref / v staged into shared memory at a time */
 #define SIM_INF (__builtin_huge_val())
 #define SIM_FULL 0xffffffffu
@@ -578,21 +581,21 @@ struct SimWarp {
 #pragma unroll
             for (int s = 0; s < NSLOT; ++s) z[s] = acc0[s] + acc1[s];
         } else {
-            // M from global memory: eight columns (8 * NSLOT independent loads per lane) in flight at a time
+            // M from global memory: SIM_MB columns (SIM_MB * NSLOT independent loads per lane) in flight at a time
             double acc0[NSLOT], acc1[NSLOT];
 #pragma unroll
             for (int s = 0; s < NSLOT; ++s) { acc0[s] = 0.0; acc1[s] = 0.0; }
             const double *mp = Mp + lane;
             int sg = 0;
-            for (; sg + 8 <= nst; sg += 8) {
-                double mv[8][NSLOT];
+            for (; sg + SIM_MB <= nst; sg += SIM_MB) {
+                double mv[SIM_MB][NSLOT];
 #pragma unroll
-                for (int e = 0; e < 8; ++e)
+                for (int e = 0; e < SIM_MB; ++e)
 #pragma unroll
                     for (int s = 0; s < NSLOT; ++s)
                         mv[e][s] = valid[s] ? __ldg(mp + (size_t)(sg + e) * R + s * 32) : 0.0;   // padded rows of M are zero: not fetched
 #pragma unroll
-                for (int e = 0; e < 8; e += 2) {
+                for (int e = 0; e < SIM_MB; e += 2) {
                     const double s0 = sm.st[sg + e], s1 = sm.st[sg + e + 1];
 #pragma unroll
                     for (int s = 0; s < NSLOT; ++s) { acc0[s] = fma(mv[e][s], s0, acc0[s]); acc1[s] = fma(mv[e + 1][s], s1, acc1[s]); }
