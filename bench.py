@@ -298,16 +298,16 @@ def main():
             "roofline": {"bound": "fp64_fma (latency-bound serial QP chain; neither hbm nor tensor, SURVEY.md 8d)",
                          "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak if fp64_peak else None,
                          "peak_source": "mpcgpu_measure_fp64_peak, measured live (MEASURED_PEAKS.json has no fp64 entry)",
-                         "kernel": "k_build + k_sim (all size buckets of one population, concurrent streams)",
+                         "kernel": "k_build + k_sim<3,16> (one launch per population)",
                          "kernel_ms": {"k_sim": sim_ms, "k_build": build_ms},
                          "algorithmic_flops_per_launch": f_survey * runs,
                          "executed_flops_per_launch": flops * runs, "executed_tflops": executed,
                          "executed_frac": executed / fp64_peak if fp64_peak else None,
                          "hbm": {"algorithmic_bytes": hbm_alg, "achieved_gbs": hbm_alg / (sim_ms + build_ms) / 1e6,
                                  "peak_gbs": peaks.get("hbm_gbs"), "frac": (hbm_alg / (sim_ms + build_ms) / 1e6) / peaks["hbm_gbs"] if peaks.get("hbm_gbs") else None},
-                         # dram__bytes_read.sum + dram__bytes_write.sum of the three k_sim launches of one population,
-                         # ncu --set full capture profiles/r1e_k_sim_summary.json (same population, GAM mode)
-                         "traffic": 45.4e6 if (args.mode == "gam" and n == 4096) else None},
+                         # dram__bytes_read.sum + dram__bytes_write.sum of the k_sim launch of one population,
+                         # ncu --set full capture profiles/r1h_k_sim_summary.json (same population, GAM mode)
+                         "traffic": 63.7e6 if (args.mode == "gam" and n == 4096) else None},
             "counters": {k: cn[k] for k in ("qp_constrained", "as_iterations", "qp_solves", "closed_loops")},
             "failed_candidates": nfail,
         }

@@ -316,11 +316,12 @@ extern "C" int mpcgpu_upload(mpcgpu_handle *h, int n, const int32_t *N, const in
     for (int c = 0; c < n; ++c) {
         const int p = N[c], m = Nu[c];
         if (p < 2 || p > L.pmax || m < 1 || m > L.mmax || m >= p) { h->hInvalid[c] = 1; continue; }
-        // One kernel image for the whole population (hard-limit plants): three concurrently running instantiations
+        // One kernel image for the whole population: three concurrently running instantiations
         // (P = 4, 8, 16, ~240 KB of SASS each) thrashed the instruction cache -- measured 16.3 ms against 10.8 ms for
-        // 4096 Shell3x3 candidates with everything on the P = 16 image.  MPCGPU_SIZE_BUCKETS=1 restores the buckets.
+        // 4096 Shell3x3 candidates with everything on the P = 16 image (Shell7x5 / k_soft: 455 -> 418 ms).
+        // MPCGPU_SIZE_BUCKETS=1 restores the buckets.
         static const bool size_buckets = getenv("MPCGPU_SIZE_BUCKETS") != nullptr;
-        const int P = (size_buckets || L.has_ov_bounds) ? sim_pad(m) : sim_pad(L.mmax), b = P == 4 ? 0 : (P == 8 ? 1 : 2);
+        const int P = size_buckets ? sim_pad(m) : sim_pad(L.mmax), b = P == 4 ? 0 : (P == 8 ? 1 : 2);
         by_p[b].push_back(c);
         if (m > mmax_p[b]) mmax_p[b] = m;
         const long long R = (long long)nu * P;
