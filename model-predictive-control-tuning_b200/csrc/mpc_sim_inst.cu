@@ -15,3 +15,13 @@ sim_kernel_t SIM_CAT(sim_kernel_nu, SIM_NU)(int P) {
     }
     return nullptr;
 }
+
+// GAM cost-only specialisation (see sim_run)
+sim_kernel_t SIM_CAT(sim_lean_nu, SIM_NU)(int P) {
+    switch (P) {
+        case 4: return k_sim<SIM_NU, 4, true>;
+        case 8: return k_sim<SIM_NU, 8, true>;
+        case 16: return k_sim<SIM_NU, 16, true>;
+    }
+    return nullptr;
+}
