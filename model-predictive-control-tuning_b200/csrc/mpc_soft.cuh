@@ -778,49 +778,25 @@ __device__ __forceinline__ int soft_run(const MpcLayout &L, const MpcTables &T, 
 #endif
     };
 
-    // ---------------- open-loop optimum (closedloop_toolbox.m:85-98) ----------------
-    if (want_ol) {
-        for (int c = tid; c < nsig; c += SOFT_THREADS) {
-            double v;
-            if (c < ny) v = T.r[(size_t)(nit - 1) * ny + c];
-            else if (c < 2 * ny) v = 0.0;
-            else v = T.v[(size_t)(nit - 1) * nd + (c - 2 * ny)];
-            sm.sig[c] = v;
-        }
-        SOFT_SYNC();
-        build_st(sm.sig, nit - 1, false);
-        const int rc = controller_move(sm.sig);
-        if (rc) status = rc;
-        // sequential cumulative sum of the moves (exact zeros stay exact, VNS2.m:183-191)
-        for (int j = tid; j < NU; j += SOFT_THREADS) {
-            double lvl = 0.0;
-            for (int c = 0; c < P; ++c) { lvl += (c < m ? sm.z[j * P + c] : 0.0); sm.uopt[j * P + c] = lvl; }
-        }
-        SOFT_SYNC();
-        if (mode == 2) {
-            double part = 0.0;
-            for (int j = tid; j < NU; j += SOFT_THREADS) {
-                if (sel < 0 || sel == j) {
-                    const double u0 = fabs(sm.uopt[j * P]);
-                    for (int c = 0; c + 1 < m && c + 1 < nit; ++c) {
-                        const double df = fabs(sm.uopt[j * P + c + 1] - sm.uopt[j * P + c]);
-                        const double xn = u0 / df;
-                        if (fabs(xn) <= 1.7976931348623157e308) part += xn * xn;
-                    }
-                }
+    // ---------------- open-loop optimum (closedloop_toolbox.m:85-98) = pass k = -1, then the closed loop (:50) with
+    // the open-loop rollout (:100) in lock-step: one loop, so that the controller and the solver inlined into it exist
+    // once in the kernel image (instruction cache) ----------------
+    for (int k = want_ol ? -1 : 0; k < nit; ++k) {
+        const bool ol = k < 0;
+        if (ol) {
+            for (int c = tid; c < nsig; c += SOFT_THREADS) {
+                double v;
+                if (c < ny) v = T.r[(size_t)(nit - 1) * ny + c];
+                else if (c < 2 * ny) v = 0.0;
+                else v = T.v[(size_t)(nit - 1) * nd + (c - 2 * ny)];
+                sm.sig[c] = v;
             }
-            jnu = soft_sum(part, sm);
+            SOFT_SYNC();
+        } else if ((k & (SIM_CH - 1)) == 0) {
+            stage_signals(k);
         }
-        // the closed loop starts from an empty active set
-        for (int a = qp.q - 1; a >= 0; --a) { qp.set_mask(sm.act[a], false); SOFT_SYNC(); }
-        qp.q = 0;   // every column of J is complement basis again (J J' = H^-1 holds for any rotation of it)
-        SOFT_SYNC();
-    }
-    // ---------------- closed loop (:50) + open-loop rollout (:100) in lock-step ----------------
-    for (int k = 0; k < nit; ++k) {
-        if ((k & (SIM_CH - 1)) == 0) stage_signals(k);
-        const double *sigrow = sm.sig + (size_t)(k & (SIM_CH - 1)) * nsig;
-        build_st(sigrow, k, true);
+        const double *sigrow = ol ? sm.sig : sm.sig + (size_t)(k & (SIM_CH - 1)) * nsig;
+        build_st(sigrow, ol ? nit - 1 : k, !ol);
         const unsigned long long it_before = qp.n_it;
 #ifdef MPC_SIMT_EMULATION
         if (tid == 0) g_soft_k = k;
@@ -828,6 +804,33 @@ __device__ __forceinline__ int soft_run(const MpcLayout &L, const MpcTables &T, 
 #endif
         const int rc = controller_move(sigrow);
         if (rc) status = rc;
+        if (ol) {
+            // sequential cumulative sum of the moves (exact zeros stay exact, VNS2.m:183-191)
+            for (int j = tid; j < NU; j += SOFT_THREADS) {
+                double lvl = 0.0;
+                for (int c = 0; c < P; ++c) { lvl += (c < m ? sm.z[j * P + c] : 0.0); sm.uopt[j * P + c] = lvl; }
+            }
+            SOFT_SYNC();
+            if (mode == 2) {
+                double part = 0.0;
+                for (int j = tid; j < NU; j += SOFT_THREADS) {
+                    if (sel < 0 || sel == j) {
+                        const double u0 = fabs(sm.uopt[j * P]);
+                        for (int c = 0; c + 1 < m && c + 1 < nit; ++c) {
+                            const double df = fabs(sm.uopt[j * P + c + 1] - sm.uopt[j * P + c]);
+                            const double xn = u0 / df;
+                            if (fabs(xn) <= 1.7976931348623157e308) part += xn * xn;
+                        }
+                    }
+                }
+                jnu = soft_sum(part, sm);
+            }
+            // the closed loop starts from an empty active set
+            for (int a = qp.q - 1; a >= 0; --a) { qp.set_mask(sm.act[a], false); SOFT_SYNC(); }
+            qp.q = 0;   // every column of J is complement basis again (J J' = H^-1 holds for any rotation of it)
+            SOFT_SYNC();
+            continue;
+        }
         if (out.trace && tid == 0) { out.trace[2 * k] = (int)(qp.n_it - it_before); out.trace[2 * k + 1] = qp.q; }
         SOFT_SYNC();
         if (tid < NU) {
