@@ -419,6 +419,8 @@ struct SimWarp {
             for (int s = 0; s < NSLOT; ++s) amask[s] = 0;
         }
         // ---- warm start on the carried set: mu = S^-1 (b_A - N_A' z_unc), shed negative multipliers ----
+        int npref = 0, pptr = 0;   // uniform: shifted constraints to be tried first (stored in sm.dflag)
+        bool first_pass = true;
         while (q > 0) {
             levels(lv);
             publish(lv);
@@ -435,12 +437,39 @@ struct SimWarp {
                 sim_wargmin(mv, mi);
                 for (int a = lane; a < q; a += 32) sm.dflag[a] = (a == mi) && (mv < -1e-12 * mumax);
                 nd_ = mi >= 0 && (mv < -1e-12 * mumax);
-            } else
-            for (int a = lane; a < q; a += 32) {
-                const int fl = sm.mu[a] < -1e-12 * mumax;
-                sm.dflag[a] = fl;
-                nd_ |= fl;
+            } else {
+                int nneg = 0;
+                for (int a0 = 0; a0 < q; a0 += 32) {
+                    const int a = a0 + lane;
+                    const int fl = a < q && sm.mu[a] < -1e-12 * mumax;
+                    if (a < q) sm.dflag[a] = fl;
+                    nneg += __popc(__ballot_sync(SIM_FULL, fl));
+                }
+                nd_ = nneg > 0;
+                if (first_pass && 2 * nneg > q && !SIM_KNOB(32)) {
+                    // Most of the carried set has the wrong sign: the plan is one that moves along the horizon
+                    // (alternating rate limits of an aggressive tuning shift by one index per sample).  Forget the
+                    // set and let the iterations below try the SHIFTED set first, constraint by constraint, through
+                    // the ordinary add path (any violated constraint is a valid pivot).
+                    __syncwarp();
+                    if (lane == 0) {
+                        int np = 0;
+                        for (int a = 0; a < q; ++a) {
+                            const int cid = sm.act[a], r = cid >> 2;
+                            if ((r & (P - 1)) > 0) sm.dflag[np++] = (cid & 3) | ((r - 1) << 2);
+                        }
+                        sm.misc[2] = np;
+                    }
+                    __syncwarp();
+                    npref = sm.misc[2];
+                    q = 0;
+#pragma unroll
+                    for (int s = 0; s < NSLOT; ++s) amask[s] = 0;
+                    it += 1;
+                    break;
+                }
             }
+            first_pass = false;
             nd_ = __any_sync(SIM_FULL, nd_);
             __syncwarp();
             if (!nd_) break;
@@ -458,6 +487,23 @@ struct SimWarp {
             levels(lv);
             double bv = -SIM_VIOL_TOL;
             int bi = -1;
+            int forced = -1;
+            while (pptr < npref) {   // next constraint of the shifted set that is violated and not yet active
+                const int cid = sm.dflag[pptr++];
+                const int r = cid >> 2, type = cid & 3;
+                double mine = 0.0;
+                int isact = 1;
+#pragma unroll
+                for (int s = 0; s < NSLOT; ++s)
+                    if (row[s] == r && valid[s]) {
+                        mine = type == 0 ? z[s] - dlo[s] : (type == 1 ? dhi[s] - z[s] : (type == 2 ? lv[s] - ulo[s] : uhi[s] - lv[s]));
+                        isact = (amask[s] >> type) & 1;
+                    }
+                const double v = __shfl_sync(SIM_FULL, mine, r & 31);
+                const int a_ = __shfl_sync(SIM_FULL, isact, r & 31);
+                if (!a_ && v < -SIM_VIOL_TOL) { forced = cid; bv = v; break; }
+            }
+            if (forced < 0)
 #pragma unroll
             for (int s = 0; s < NSLOT; ++s) {
                 if (!valid[s]) continue;
@@ -469,7 +515,8 @@ struct SimWarp {
                     if (sl[type] < bv || (sl[type] == bv && bi >= 0 && id < bi)) { bv = sl[type]; bi = id; }
                 }
             }
-            {   // pivot rule: among the violated constraints take the EARLIEST horizon index first (then the most
+            if (forced >= 0) bi = forced;
+            else {   // pivot rule: among the violated constraints take the EARLIEST horizon index first (then the most
                 // violated).  Any violated constraint is a valid Goldfarb-Idnani pivot; walking the horizon in time
                 // order follows how rate/level saturation propagates and avoids most of the add/drop churn of the
                 // most-violated rule.  One integer warp reduction finds that index -- and tells when nothing is violated.
@@ -479,8 +526,8 @@ struct SimWarp {
 #ifndef SIM_PIVOT_MOST_VIOLATED
                 if (!most_violated && cmine != cmin) { bv = -SIM_VIOL_TOL; bi = -1; }
 #endif
+                sim_wargmin(bv, bi);
             }
-            sim_wargmin(bv, bi);
             const int p = bi;
             SIM_DBG("  pivot %c%d.%d viol %.3e (q=%d)\n", "dDuU"[p & 3], (p >> 2) / P, (p >> 2) % P, bv, q);
             double sp = bv, mu_p = 0.0;
