@@ -25,6 +25,9 @@
 
 #define SIM_VIOL_TOL 1e-10
 #define SIM_DEP_TOL 1e-13
+#ifndef SIM_SHIFT_DEN
+#define SIM_SHIFT_DEN 2   /* guided shifted restart when more than 1/SIM_SHIFT_DEN of the carried multipliers are negative */
+#endif
 #define SIM_CHURN 24   /* iterations per constrained QP above which a run switches its pivot rule */
 #define SIM_REFRESH 96 /* Givens removals after which the active-set factor is rebuilt from W */
 #ifndef SIM_MB
@@ -446,7 +449,7 @@ struct SimWarp {
                     nneg += __popc(__ballot_sync(SIM_FULL, fl));
                 }
                 nd_ = nneg > 0;
-                if (first_pass && 2 * nneg > q && !SIM_KNOB(32)) {
+                if (first_pass && SIM_SHIFT_DEN * nneg > q && !SIM_KNOB(32)) {
                     // Most of the carried set has the wrong sign: the plan is one that moves along the horizon
                     // (alternating rate limits of an aggressive tuning shift by one index per sample).  Forget the
                     // set and let the iterations below try the SHIFTED set first, constraint by constraint, through
