@@ -98,6 +98,37 @@ def host_threads():
         return max(1, os.cpu_count() or 1)
 
 
+def other_configs():
+    """One population of each of the other BASELINE.json configurations on this GPU, through the same public API
+    (host arrays in and out, wall clock; after one warm-up call).  Context for the headline line, not part of it."""
+    import mpcgpu
+    out = {}
+    try:
+        p7 = mpcgpu.shell7x5(); e7 = mpcgpu.Evaluator(p7, device=0)
+        P7 = mpcgpu.synthetic_population(p7, 2048, seed=0, wlo=1e-2)
+        e7.eval_batch(*[a[:64] for a in P7], mode="gam")
+        t0 = time.perf_counter(); o7 = e7.eval_batch(*P7, mode="gam"); dt = time.perf_counter() - t0
+        out["shell7x5_soft_constraints"] = {"candidates": 2048, "candidates_per_s": 2048 / dt, "failed": int((o7["status"] != 0).sum()),
+                                            "weights": "lambda log-uniform [1e-2, 10], delta = 0 (band control)"}
+        e7.close()
+        pd = mpcgpu.woodberry_dtc(); ed = mpcgpu.DtcEvaluator(pd, device=0)
+        Pd = mpcgpu.synthetic_dtc_population(pd, 16384, seed=0)
+        fil = [mpcgpu.mimo_filter(pd.pnz, float(a), float(r)) for a, r in zip(Pd[4][:256], Pd[5][:256])] * 64
+        ed.eval_batch(*[a[:64] for a in Pd[:4]], filters=fil[:64])
+        t0 = time.perf_counter(); od = ed.eval_batch(*Pd[:4], filters=fil); dt = time.perf_counter() - t0
+        out["dtc_gpc_sweep"] = {"candidates": 16384, "candidates_per_s": 16384 / dt, "failed": int((od["status"] != 0).sum())}
+        ed.close()
+        pn = mpcgpu.vandevusse(); en = mpcgpu.NmpcEvaluator(pn, device=0)
+        Pn = mpcgpu.synthetic_nmpc_population(pn, 4096, seed=0)
+        en.eval_batch(*[a[:64] for a in Pn], mode="gam")
+        t0 = time.perf_counter(); on = en.eval_batch(*Pn, mode="gam"); dt = time.perf_counter() - t0
+        out["vandevusse_nmpc"] = {"candidates": 4096, "candidates_per_s": 4096 / dt, "failed": int((~np.isin(on["status"], (0, 5))).sum())}
+        en.close()
+    except Exception as exc:   # context only: never fail the headline line
+        out["error"] = repr(exc)
+    return out
+
+
 def cpu_reference_rate(prob, N, Nu, delta, lam, mode, budget_s=12.0, nthreads=0):
     """Times the CPU oracle (the port of the reference's path) on a bounded sample of the same population."""
     from oracle import oracle as orc
@@ -160,6 +191,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pop", type=int, default=4096, help="candidates per GPU")
     ap.add_argument("--mode", default="gam", choices=["gam", "vns"])
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the Shell7x5 / DTC-GPC / NMPC context numbers")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--fixed", default="", help="p,m : pin every candidate's horizons (diagnostic populations)")
     ap.add_argument("--weights", default="", help="lo,hi : log-uniform weight range (default 1e-4,10)")
@@ -306,8 +338,8 @@ def main():
                          "hbm": {"algorithmic_bytes": hbm_alg, "achieved_gbs": hbm_alg / (sim_ms + build_ms) / 1e6,
                                  "peak_gbs": peaks.get("hbm_gbs"), "frac": (hbm_alg / (sim_ms + build_ms) / 1e6) / peaks["hbm_gbs"] if peaks.get("hbm_gbs") else None},
                          # dram__bytes_read.sum + dram__bytes_write.sum of the k_sim launch of one population,
-                         # ncu --set full capture profiles/r1h_k_sim_summary.json (same population, GAM mode)
-                         "traffic": 63.7e6 if (args.mode == "gam" and n == 4096) else None},
+                         # ncu --set full capture profiles/r1i_k_sim_summary.json (same population, GAM mode)
+                         "traffic": 67.7e6 if (args.mode == "gam" and n == 4096) else None},
             "counters": {k: cn[k] for k in ("qp_constrained", "as_iterations", "qp_solves", "closed_loops")},
             "failed_candidates": nfail,
         }
@@ -315,6 +347,8 @@ def main():
             v, cores, ns = cpu_reference_rate(prob, N, Nu, delta, lam, args.mode)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"first {ns} candidates of the same seeded population, oracle/mpc_oracle.c, OpenMP over candidates"}
+        if world == 1 and not args.no_other_configs:
+            line["other_configs"] = other_configs()
         print(json.dumps(line), flush=True)
     ev.close()
     if world > 1:
