@@ -28,6 +28,32 @@
 #ifndef SIM_SHIFT_DEN
 #define SIM_SHIFT_DEN 2   /* guided shifted restart when more than 1/SIM_SHIFT_DEN of the carried multipliers are negative */
 #endif
+#define SIM_MISC_INTS 20  /* sm.misc: [2] scratch of the shifted restart, [3..18] state of the two-phase mode */
+#define SIM_PP_ON 3
+#define SIM_PP_QS 9       /* [9], [10]: active-set sizes of the two parked factors */
+#define SIM_PP_CUR 4      /* slot that belongs to the carried factor */
+#define SIM_PP_DIRTY 11   /* the carried factor differs from its slot */
+#define SIM_PP_NCON 12    /* constrained-sample counter at the last bookkeeping call */
+#define SIM_PP_STREAK 13  /* consecutive constrained samples with a bookkeeping call */
+#define SIM_PP_FIRST 14   /* the next re-entry is the first of the mode */
+#define SIM_PP_BAD 15     /* consecutive expensive re-entries */
+#define SIM_PP_MATCH 16   /* the previous bookkeeping call saw the A B A pattern */
+#define SIM_PP_BACK 17    /* back-off length after failed episodes */
+#define SIM_PP_WAIT 18    /* constrained-sample count before which the mode is not entered again */
+#define SIM_PP_GOOD 19    /* this episode had a cheap re-entry */
+#define SIM_PP_SIG1 5
+#define SIM_PP_SIG2 6
+#define SIM_PP_COUNT 7   /* exchanges of this run (diagnostics) */
+#define SIM_PP_REENTERED 8
+#ifndef SIM_PP_BADIT
+#define SIM_PP_BADIT 4    /* a re-entry that needs this many iterations is no better than the carried set */
+#endif
+#define SIM_PP_GOODIT 2   /* a re-entry that needs at most this many paid off */
+#ifndef SIM_PP_DOUBLE_MATCH
+#define SIM_PP_DOUBLE_MATCH 0   /* 1: enter on A B A B instead of A B A */
+#endif
+#define SIM_PP_STREAK_MIN 3 /* bookkeeping calls in a row (= expensive solves at consecutive constrained samples) before the mode may be entered, counted from 0 */
+#define SIM_PP_HEAVY 6    /* active-set iterations in one QP from which the warm start counts as torn down */
 #define SIM_CHURN 24   /* iterations per constrained QP above which a run switches its pivot rule */
 #define SIM_REFRESH 96 /* Givens removals after which the active-set factor is rebuilt from W */
 #ifndef SIM_MB
@@ -76,6 +102,13 @@ static MPC_HD size_t sim_scratch_doubles(int R) {
     const int qc = sim_qc(R);
     return 2 * (size_t)(R - qc) * R;   // V columns and (full-length) Li rows beyond QC
 }
+// per-run parking slot of the two-phase mode (SimWarp::exchange): V columns (QC x R), Li rows (QC x QC), the
+// constraint ids (QC ints), the per-lane constraint masks.  Kept in a region of its own: appending it to the spill
+// area changed that area's stride to ~32 KB and cost 4 % on its own (gpurun_out/ab21.log).
+static MPC_HD size_t sim_slot_doubles(int R) {
+    const int qc = sim_qc(R);
+    return 2 * ((size_t)qc * R + (size_t)qc * qc + 32);   // two slots, see sim_pp_exchange
+}
 static MPC_HD size_t sim_smem_doubles(const MpcLayout &L, int nu, int P) {
     const int R = nu * P, qc = sim_qc(R), nch = L.ny * L.nw, HL = sim_hl(L);
     size_t n = sim_m_in_smem(P) ? (size_t)L.nst * R : 0;   // M
@@ -89,7 +122,7 @@ static MPC_HD size_t sim_smem_doubles(const MpcLayout &L, int nu, int P) {
     n += 6 * (size_t)R;                       // z, lvl, w, wsc, w2, w2sc
     n += 4 * (size_t)R;                       // g, l, rr, mu
     n += (size_t)qc * R + (size_t)qc * qc;    // V, Li (full stride)
-    n += (2 * nch + L.nst + 2 * R + 8 + 1) / 2 + 1;   // ints: chd, chj, role, act, dflag, misc
+    n += (2 * nch + L.nst + 2 * R + SIM_MISC_INTS + 1) / 2 + 1;   // ints: chd, chj, role, act, dflag, misc
     return n;
 }
 
@@ -133,6 +166,108 @@ __device__ __forceinline__ double sim_pick(const double (&u)[NU], int j) {
     return r;
 }
 
+// ---- two-phase mode (period-2 limit cycles) ----------------------------------------------------------------
+// A tuning that limit-cycles with period 2 (rate limits hit in alternating directions) has TWO active sets, one per
+// phase; the set carried from the previous sample is then always the wrong one and is torn down and rebuilt
+// constraint by constraint, 8-17 iterations per sample for 491 samples (the heaviest runs of a 32768-candidate
+// population).  The factor (V, Li) depends on the set only, not on the sample's data, so the set of two samples
+// ago is parked in global memory and re-entered: a warm start that is usually optimal as it stands.
+// Both routines are cold and deliberately NOT inlined, with their state in shared memory (sm.misc) and the masks
+// passed packed in a register: the closed-loop kernel is instruction-cache and register bound,
+// anything added to its hot body costs every run.
+#ifdef MPC_SIMT_EMULATION
+#define SIM_COLD static
+#else
+#define SIM_COLD static __device__ __noinline__
+#endif
+// Re-enter the factor of the other phase.  Each phase has a slot in global memory: V (QC x R) followed by Li (QC x QC)
+// as in shared memory (vli), then QC constraint ids and 32 packed per-lane masks.  The carried factor is written to
+// its slot only if the last solve changed it (in a settled cycle both factors are read-only: loads that stay in L2,
+// no stores to evict the M tables of the neighbouring runs).  Returns the new active-set size in bits [0,8) and this
+// lane's constraint masks (4 bits per row slot) from bit 8.
+SIM_COLD int sim_pp_exchange(double *vli, int *act, int *misc, double *slot, int lane, int q, int masks, int R, int QC) {
+    const size_t S = (size_t)QC * R + (size_t)QC * QC + 32;   // doubles per slot (the int part: QC + 32 ints <= 32 doubles)
+    const int cur = misc[SIM_PP_CUR], dirty = misc[SIM_PP_DIRTY];
+    double *sc = slot + (size_t)cur * S, *so = slot + (size_t)(1 - cur) * S;
+    int *ic = (int *)(sc + (size_t)QC * R + (size_t)QC * QC), *io = (int *)(so + (size_t)QC * R + (size_t)QC * QC);
+    const int first = misc[SIM_PP_FIRST];   // first sample of the mode: park the carried factor, keep it as the warm start
+    const int qb = first ? 0 : misc[SIM_PP_QS + 1 - cur];
+    if (dirty) {
+        const int nv = q * R, n = q * (R + QC);
+#pragma unroll 1
+        for (int j = lane; j < n; j += 32) {
+            const int idx = j < nv ? j : QC * R + (j - nv);
+            sc[idx] = vli[idx];
+        }
+        if (lane < QC) ic[lane] = act[lane];
+        ic[QC + lane] = masks;
+    }
+    __syncwarp();
+    {   // rows [0, qb) of V and of Li as ONE loop over a virtual index, four independent global loads in flight per
+        // pass (a dependent load per element made the re-entry cost ten active-set iterations)
+        const int nv = qb * R, n = qb * (R + QC);
+#pragma unroll 1
+        for (int j0 = lane; j0 < n; j0 += 128) {
+            double g[4];
+            int idx[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int j = j0 + 32 * e < n ? j0 + 32 * e : j0;
+                idx[e] = j < nv ? j : QC * R + (j - nv);
+                g[e] = so[idx[e]];
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (j0 + 32 * e < n) vli[idx[e]] = g[e];
+        }
+    }
+    if (lane < qb) act[lane] = io[lane];
+    const int theirs = qb > 0 ? io[QC + lane] : 0;   // an empty slot holds nothing yet
+    if (lane == 0) {
+        misc[SIM_PP_QS + cur] = q; misc[SIM_PP_CUR] = 1 - cur; misc[SIM_PP_DIRTY] = first;
+        misc[SIM_PP_REENTERED] = qb > 0; misc[SIM_PP_COUNT] += qb > 0; misc[SIM_PP_FIRST] = 0;
+    }
+    __syncwarp();
+    return first ? (q | (masks << 8)) : (qb | (theirs << 8));
+}
+// End of a constrained solve that took `it` iterations and ended on `q` constraints: an expensive solve that ends on
+// the set of two samples ago, and not on the previous one, is a period-2 cycle -- start parking.  Leave the mode
+// again when a re-entered set turns out as expensive as a torn-down one.
+SIM_COLD void sim_pp_update(const int *act, int *misc, int lane, int q, int it, int QC, int ncon) {
+    unsigned hsh = 0u;   // order-independent signature of the final active set
+    for (int a = lane; a < q; a += 32) hsh ^= ((unsigned)act[a] + 1u) * 2654435761u;
+    const int sig = (int)(__reduce_xor_sync(SIM_FULL, hsh) ^ ((unsigned)q << 26));
+    const int s1 = misc[SIM_PP_SIG1], s2 = misc[SIM_PP_SIG2], on = misc[SIM_PP_ON], reentered = misc[SIM_PP_REENTERED];
+    const int last = misc[SIM_PP_NCON], streak = misc[SIM_PP_STREAK];   // consecutive constrained samples seen here
+    __syncwarp();
+    if (lane == 0) {
+        const int st = (ncon == last + 1) ? streak + 1 : 0;
+        misc[SIM_PP_NCON] = ncon; misc[SIM_PP_STREAK] = st;
+        misc[SIM_PP_SIG2] = s1; misc[SIM_PP_SIG1] = sig;
+        const int match = st >= SIM_PP_STREAK_MIN && sig == s2 && sig != s1;   // A B A at the end of a row of expensive solves
+        const int match_prev = misc[SIM_PP_MATCH];
+        misc[SIM_PP_MATCH] = match;
+        if (on) {
+            if (it > 0) misc[SIM_PP_DIRTY] = 1;
+            if (reentered) {   // a re-entered set that is as expensive as a torn-down one: twice in a row, or very
+                const int bad = it >= SIM_PP_BADIT ? misc[SIM_PP_BAD] + 1 : 0;
+                misc[SIM_PP_BAD] = bad;
+                if (it <= SIM_PP_GOODIT) misc[SIM_PP_GOOD] = 1;
+                if (bad >= 2 || it >= 2 * SIM_PP_HEAVY) {
+                    // leave; an episode without a single cheap re-entry was a false alarm: wait 16, 32, .. 256
+                    // constrained samples before the next one
+                    const int back0 = misc[SIM_PP_BACK];
+                    const int back = misc[SIM_PP_GOOD] ? 0 : (back0 ? (back0 < 256 ? 2 * back0 : 256) : 16);
+                    misc[SIM_PP_ON] = 0; misc[SIM_PP_BACK] = back; misc[SIM_PP_WAIT] = ncon + back;
+                }
+            }
+        } else if (match && (match_prev || !SIM_PP_DOUBLE_MATCH) && ncon >= misc[SIM_PP_WAIT] && q <= QC && !SIM_KNOB(64)) {
+            misc[SIM_PP_ON] = 1; misc[SIM_PP_FIRST] = 1; misc[SIM_PP_CUR] = 0; misc[SIM_PP_DIRTY] = 1; misc[SIM_PP_BAD] = 0; misc[SIM_PP_GOOD] = 0;
+        }
+    }
+    __syncwarp();
+}
+
 // Everything one warp needs to carry through the run; template so that R, P, NSLOT are constants.
 template <int NU, int P>
 struct SimWarp {
@@ -158,6 +293,9 @@ struct SimWarp {
     int qmax;
     int n_rot;      // uniform: Givens removals since the factor was last rebuilt from W
     int churn;      // uniform: 1 once the run has switched to most-violated-first pivoting (qp_solve)
+    // period-2 limit cycles (bang-bang tunings): the factor of the OTHER phase is parked in global memory behind the
+    // spill area (exchange()); the mode's state lives in shared memory (sm.misc + SIM_PP_*), not in registers
+    double *slot;   // uniform: this run's parking slot (global memory), nullptr: mode off
 
     __device__ __forceinline__ SimWarp(const MpcLayout &L_) : L(L_) {}
 
@@ -421,6 +559,21 @@ struct SimWarp {
 #pragma unroll
             for (int s = 0; s < NSLOT; ++s) amask[s] = 0;
         }
+        if (sm.misc[SIM_PP_ON]) {   // two-phase mode: re-enter the factor of two samples ago (first sample of the
+            // mode: the slot is empty, the carried factor is parked and this sample starts cold -- its carried set
+            // would have been torn down anyway)
+            if (q > QC) { __syncwarp(); if (lane == 0) sm.misc[SIM_PP_ON] = 0; }
+            if (q <= QC) {
+                int masks = 0;
+#pragma unroll
+                for (int s = 0; s < NSLOT; ++s) masks |= amask[s] << (4 * s);
+                const int r_ = sim_pp_exchange(sm.V, sm.act, sm.misc, slot, lane, q, masks, R, QC);
+                q = r_ & 255;
+#pragma unroll
+                for (int s = 0; s < NSLOT; ++s) amask[s] = (r_ >> (8 + 4 * s)) & 15;
+            }
+            __syncwarp();
+        }
         // ---- warm start on the carried set: mu = S^-1 (b_A - N_A' z_unc), shed negative multipliers ----
         int npref = 0, pptr = 0;   // uniform: shifted constraints to be tried first (stored in sm.dflag)
         bool first_pass = true;
@@ -598,6 +751,9 @@ struct SimWarp {
         n_it += it;
         if (q > qmax) qmax = q;
         SIM_DBGSET("final");
+        // two-phase mode bookkeeping (cold, not inlined): only after an expensive solve or inside the mode -- called after
+        // every constrained solve it cost all runs 4 % (gpurun_out/d28*.log)
+        if (slot && (it >= SIM_PP_HEAVY || sm.misc[SIM_PP_ON])) sim_pp_update(sm.act, sm.misc, lane, q, it, QC, (int)n_con);
         return 0;
     }
 
@@ -686,7 +842,7 @@ struct SimWarp {
 template <int NU, int P, bool LEAN = false>
 __device__ __forceinline__ int sim_run(const MpcLayout &L, const MpcTables &T, int m, const double *__restrict__ Mg,
                                        const double *__restrict__ Wg, int mode_arg, int sel, double *smem, double *gscr,
-                                       const MpcRunOut &out_arg) {
+                                       const MpcRunOut &out_arg, double *pslot = nullptr) {
     const int mode = LEAN ? 1 : mode_arg;
     MpcRunOut out = out_arg;
     if (LEAN) { out.y = nullptr; out.u = nullptr; out.ys = nullptr; out.uopt = nullptr; out.diag = nullptr; out.trace = nullptr; }
@@ -719,6 +875,11 @@ __device__ __forceinline__ int sim_run(const MpcLayout &L, const MpcTables &T, i
         sm.act = ip; ip += R; sm.dflag = ip; ip += R; sm.misc = ip;
     }
     wp.gscr = gscr; wp.W = Wg; wp.lane = lane; wp.m = m; wp.q = 0; wp.n_con = 0; wp.n_it = 0; wp.qmax = 0; wp.n_rot = 0; wp.churn = 0;
+#ifdef SIM_NO_TWO_PHASE
+    wp.slot = nullptr;
+#else
+    wp.slot = pslot;
+#endif
 #pragma unroll
     for (int s = 0; s < NSLOT; ++s) {
         const int r = s * 32 + lane;
@@ -748,6 +909,7 @@ __device__ __forceinline__ int sim_run(const MpcLayout &L, const MpcTables &T, i
     for (int j = lane; j < NU; j += 32) {
         sm.bnd[4 * j + 0] = L.dumin[j]; sm.bnd[4 * j + 1] = L.dumax[j]; sm.bnd[4 * j + 2] = L.umin[j]; sm.bnd[4 * j + 3] = L.umax[j];
     }
+    if (lane < SIM_MISC_INTS) sm.misc[lane] = lane == SIM_PP_SIG2 ? 1 : 0;
     // role of every deviation coordinate: kind | a << 2 | b << 12  (kind 0: x_ch, 1: hist(j=a, lag=b), 2: e_i)
     for (int col = lane; col < nst; col += 32) {
         int role;
@@ -957,6 +1119,6 @@ __device__ __forceinline__ int sim_run(const MpcLayout &L, const MpcTables &T, i
         atomicAdd(out.counters + 0, wp.n_con);
         atomicAdd(out.counters + 1, wp.n_it);
     }
-    if (out.diag && lane == 0) { out.diag[0] = wp.n_con; out.diag[1] = wp.n_it; out.diag[2] = (unsigned long long)wp.qmax; }
+    if (out.diag && lane == 0) { out.diag[0] = wp.n_con; out.diag[1] = wp.n_it; out.diag[2] = (unsigned long long)wp.qmax | ((unsigned long long)sm.misc[SIM_PP_COUNT] << 32); }
     return status;
 }

@@ -17,6 +17,8 @@ struct DevCand {
     int *bstatus;  // builder status per candidate
     double *scratch;  // per-run spill area of the closed-loop kernel (V / Li beyond QC)
     long long scratch_stride;
+    double *slot;     // per-run parking slots of the two-phase mode (sim_slot_doubles), or nullptr
+    long long slot_stride;
 };
 
 struct DevOut {
@@ -60,7 +62,8 @@ __global__ void __launch_bounds__(32) k_sim(const MpcLayout L, const MpcTables T
     const long long t_start = clock64();
     const int sel = mode == 2 ? (square ? run : -1) : -2;
     double *gscr = C.scratch ? C.scratch + (size_t)(item0 + item) * C.scratch_stride : nullptr;
-    const int st = sim_run<NU, P, LEAN>(L, T, m, C.M + C.offM[c], C.W + C.offW[c], mode, sel, smem_s, gscr, out);
+    double *pslot = C.slot ? C.slot + (size_t)(item0 + item) * C.slot_stride : nullptr;
+    const int st = sim_run<NU, P, LEAN>(L, T, m, C.M + C.offM[c], C.W + C.offW[c], mode, sel, smem_s, gscr, out, pslot);
     if (st != 0 && (threadIdx.x & 31) == 0) atomicMax(O.status + c, st);
     if (out.diag && (threadIdx.x & 31) == 0) out.diag[3] = (unsigned long long)(clock64() - t_start);
 }

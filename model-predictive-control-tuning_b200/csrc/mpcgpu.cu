@@ -345,11 +345,16 @@ extern "C" int mpcgpu_upload(mpcgpu_handle *h, int n, const int32_t *N, const in
         // heaviest first, so that the longest closed loops start at t = 0: work grows with the number of
         // moves and with how hard the controller pushes against the MV limits (large delta / small lambda)
         std::vector<double> score(n, 0.0);
+        int dead_max = 0;
+        for (int ch = 0; ch < L.ny * L.nw; ++ch) dead_max = std::max(dead_max, (int)L.d[ch]);
         for (int c : by_p[b]) {
             double dmax = 0.0, lmin = 1e300;
             for (int i = 0; i < ny; ++i) dmax = std::max(dmax, std::fabs(delta[(size_t)c * ny + i]));
             for (int j = 0; j < nu; ++j) lmin = std::min(lmin, std::fabs(lambda[(size_t)c * nu + j]));
             score[c] = std::log10(dmax / (lmin + 1e-300) + 1e-300) + 0.15 * Nu[c];
+            // a prediction horizon that barely clears the longest dead time tends to limit-cycle against the rate
+            // limits: a constrained QP at every sample, among the longest runs of a population
+            if (N[c] <= dead_max + 2) score[c] += 2.0;
         }
         std::stable_sort(by_p[b].begin(), by_p[b].end(), [&](int x, int y) { return score[x] > score[y]; });
         mpcgpu_handle::Bucket bk{4 << b, mmax_p[b], (int)h->hOrder.size(), (int)by_p[b].size()};
@@ -415,9 +420,16 @@ extern "C" int mpcgpu_run(mpcgpu_handle *h, int cost_mode, int want_traj, void *
         if (sd > scr_stride) scr_stride = sd;
         scr_items += (long long)bk.count * runs;
     }
-    if (scr_stride > 0) CK(h->dScratch.ensure((size_t)(scr_stride * scr_items + 1)));
+    long long slot_stride = 0;
+    for (const auto &bk : h->buckets) slot_stride = std::max(slot_stride, (long long)sim_slot_doubles(nu * bk.P));
+    // the block kernel of the soft-constraint path has no such mode; MPCGPU_TWO_PHASE=0 switches it off (A/B runs)
+    const char *tp_env = getenv("MPCGPU_TWO_PHASE");
+    const bool two_phase = !L.has_ov_bounds && !(tp_env && atoi(tp_env) == 0);
+    // one allocation: [spill areas | parking slots]
+    if (scr_stride > 0 || two_phase) CK(h->dScratch.ensure((size_t)((scr_stride + (two_phase ? slot_stride : 0)) * scr_items + 1)));
     DevCand C{h->dN.p, h->dNu.p, h->dDelta.p, h->dLambda.p, h->dOffM.p, h->dOffW.p, h->dM.p, h->dW.p, h->dBStatus.p,
-              scr_stride > 0 ? h->dScratch.p : nullptr, scr_stride};
+              scr_stride > 0 ? h->dScratch.p : nullptr, scr_stride,
+              two_phase ? h->dScratch.p + scr_stride * scr_items : nullptr, slot_stride};
     DevOut O{h->dCost.p, h->dPart.p, h->dStatus.p, h->dCounters.p,
              want_traj ? h->dY.p : nullptr, want_traj ? h->dU.p : nullptr, want_traj ? h->dYs.p : nullptr,
              want_traj ? h->dUopt.p : nullptr, nullptr};

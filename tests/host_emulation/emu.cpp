@@ -30,10 +30,11 @@ extern "C" long long emu_reappends() { long long r = g_sim_reappends; g_sim_reap
 template <int NU>
 static int sim_p(int P, const MpcLayout &L, const MpcTables &T, int m, const double *Mg, const double *Wg, int mode, int sel,
                  double *smem, double *gscr, const MpcRunOut &out) {
+    double *slot = gscr + sim_scratch_doubles(NU * P);
     switch (P) {
-        case 4: return sim_run<NU, 4>(L, T, m, Mg, Wg, mode, sel, smem, gscr, out);
-        case 8: return sim_run<NU, 8>(L, T, m, Mg, Wg, mode, sel, smem, gscr, out);
-        default: return sim_run<NU, 16>(L, T, m, Mg, Wg, mode, sel, smem, gscr, out);
+        case 4: return sim_run<NU, 4>(L, T, m, Mg, Wg, mode, sel, smem, gscr, out, slot);
+        case 8: return sim_run<NU, 8>(L, T, m, Mg, Wg, mode, sel, smem, gscr, out, slot);
+        default: return sim_run<NU, 16>(L, T, m, Mg, Wg, mode, sel, smem, gscr, out, slot);
     }
 }
 static int sim_dispatch(int nu, int P, const MpcLayout &L, const MpcTables &T, int m, const double *Mg, const double *Wg,
@@ -79,7 +80,7 @@ static int run_block(int nu, int P, const MpcLayout &L, const MpcTables &T, int 
 static int run_warp(int nu, int P, const MpcLayout &L, const MpcTables &T, int m, const double *Mg, const double *Wg, int mode,
                     int sel, const MpcRunOut &out) {
     std::vector<double> smem(sim_smem_doubles(L, nu, P) + 8, std::nan(""));   // NaN-poison: catches reads of unwritten shared memory
-    std::vector<double> gscr(sim_scratch_doubles(nu * P) + 8, std::nan(""));
+    std::vector<double> gscr(sim_scratch_doubles(nu * P) + sim_slot_doubles(nu * P) + 8, std::nan(""));
     int status[32];
     simt_run_warp([&]() {
         status[threadIdx.x] = sim_dispatch(nu, P, L, T, m, Mg, Wg, mode, sel, smem.data(), gscr.data(), out);
@@ -146,4 +147,11 @@ extern "C" int emu_eval_batch(const mpcgpu_problem *pb, int n, const int *N, con
         if (status) status[c] = st;
     }
     return 0;
+}
+
+// shared-memory footprint of one closed-loop run (bytes) for padded control horizon P: occupancy bookkeeping
+extern "C" long long emu_sim_smem_bytes(const mpcgpu_problem *pb, int P) {
+    MpcHostTables ht;
+    if (!mpc_build_tables(*pb, ht).empty()) return -1;
+    return (long long)(sim_smem_doubles(ht.L, ht.L.nu, P) * sizeof(double));
 }

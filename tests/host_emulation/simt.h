@@ -90,6 +90,14 @@ static inline unsigned __reduce_min_sync(unsigned, unsigned v) {
     simt_warp->bar.arrive_and_wait();
     return r;
 }
+static inline unsigned __reduce_xor_sync(unsigned, unsigned v) {
+    simt_warp->vote[threadIdx.x & 31] = v;
+    simt_warp->bar.arrive_and_wait();
+    unsigned r = 0u;
+    for (int i = 0; i < 32; ++i) r ^= simt_warp->vote[i];
+    simt_warp->bar.arrive_and_wait();
+    return r;
+}
 static inline long long __double_as_longlong(double d) { long long r; std::memcpy(&r, &d, 8); return r; }
 static inline double __longlong_as_double(long long l) { double r; std::memcpy(&r, &l, 8); return r; }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }

@@ -81,3 +81,26 @@ def test_soft_output_constraints_block_kernel():
         y, u, ys, uo, rc, _ = orc.closedloop(op, N[c], Nu[c], dl[c], lm[c])
         for a, b in zip(tr, (y, u, ys, uo)):
             assert np.abs(a[c] - b).max() < TOL_TRAJ
+
+
+def test_two_phase_limit_cycle_reentry():
+    """A bang-bang tuning (N = 8, Nu = 6, candidate 4169 of the 32768-candidate seeded population) limit-cycles with
+    period 2: the closed-loop kernel parks the factor of the other phase and re-enters it (SimWarp::exchange).
+    Same optimum as the oracle, and far fewer active-set iterations than with the mode disabled (knob 64)."""
+    p = short(shell3x3(2), 110)
+    op = orc.OracleProblem(p)
+    N = np.array([8], dtype=np.int32); Nu = np.array([6], dtype=np.int32)
+    dl = np.array([[5.34255979, 0.03985835, 0.00996119]]); lm = np.array([[0.01538541, 0.00029207, 0.00017591]])
+    y, u, ys, uo, rc, _ = orc.closedloop(op, 8, 6, dl[0], lm[0])
+    assert rc == 0
+    g1, st1, cnt, tr = emu.eval_batch(p, N, Nu, dl, lm, "gam", traj=True)
+    assert st1[0] == 0
+    for a, b in zip(tr[:2], (y, u)):
+        assert np.abs(a[0] - b).max() < TOL_TRAJ
+    emu.lib().emu_set_knob(64)
+    try:
+        g2, st2, cnt2, _ = emu.eval_batch(p, N, Nu, dl, lm, "gam")
+    finally:
+        emu.lib().emu_set_knob(0)
+    assert np.allclose(g1, g2, rtol=1e-9)
+    assert int(cnt2[1]) > 400 and int(cnt[1]) < int(cnt2[1]) // 3, (cnt, cnt2)

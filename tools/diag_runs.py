@@ -10,7 +10,7 @@ ev.lib.mpcgpu_debug_enable_diag(ev.h, 1)
 for _ in range(2): out = ev.eval_batch(N, Nu, dl, lm, mode='gam')
 d = np.zeros((NPOP,4), dtype=np.uint64)
 rc = ev.lib.mpcgpu_debug_get_diag(ev.h, d.ctypes.data_as(C.c_void_p)); print('rc', rc)
-cyc = d[:,3].astype(float); its = d[:,1].astype(float); con = d[:,0].astype(float); qm = d[:,2].astype(float)
+cyc = d[:,3].astype(float); its = d[:,1].astype(float); con = d[:,0].astype(float); qm = (d[:,2] & np.uint64(0xffffffff)).astype(float); xc = (d[:,2] >> np.uint64(32)).astype(float); print('re-entries: total %d, runs with any %d' % (xc.sum(), (xc > 0).sum()))
 print('cycles: mean %.3g median %.3g p99 %.3g max %.3g (ms at 1.965GHz: max %.2f)'%(cyc.mean(), np.median(cyc), np.percentile(cyc,99), cyc.max(), cyc.max()/1.965e6))
 print('counters', ev.counters())
 top = np.argsort(-cyc)[:12]
@@ -22,4 +22,4 @@ for P,(lo,hi) in {4:(1,4),8:(5,8),16:(9,15)}.items():
     if len(sel): print('P',P,'fast-only candidates', len(sel), 'cycles/step median %.0f'%(np.median(cyc[sel])/500))
 # regression cycles vs its, con
 A = np.stack([np.ones(NPOP), con, its, its*qm],1); coef,*_ = np.linalg.lstsq(A, cyc, rcond=None); print('fit cyc ~ %.3g + %.3g*con + %.3g*its + %.3g*its*qmax'%tuple(coef))
-np.save('gpurun_out/diag.npy', d)
+np.save('gpurun_out/diag_%s.npy' % (sys.argv[2] if len(sys.argv) > 2 else 'x'), d)
