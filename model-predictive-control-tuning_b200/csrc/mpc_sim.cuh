@@ -55,7 +55,7 @@
 #define SIM_PP_STREAK_MIN 3 /* bookkeeping calls in a row (= expensive solves at consecutive constrained samples) before the mode may be entered, counted from 0 */
 #define SIM_PP_HEAVY 6    /* active-set iterations in one QP from which the warm start counts as torn down */
 #define SIM_CHURN 24   /* iterations per constrained QP above which a run switches its pivot rule */
-#define SIM_REFRESH 96 /* Givens removals after which the active-set factor is rebuilt from W */
+#define SIM_REFRESH 96 /* Givens removals after which the factor of the soft-constraint kernel (mpc_soft.cuh) is refreshed */
 #ifndef SIM_MB
 #define SIM_MB 18 /* columns of M in flight per batch when M is read from global memory (P = 16) */
 #endif
@@ -291,7 +291,6 @@ struct SimWarp {
     int q;          // uniform: carried active-set size
     unsigned long long n_con, n_it;
     int qmax;
-    int n_rot;      // uniform: Givens removals since the factor was last rebuilt from W
     int churn;      // uniform: 1 once the run has switched to most-violated-first pivoting (qp_solve)
     // period-2 limit cycles (bang-bang tunings): the factor of the OTHER phase is parked in global memory behind the
     // spill area (exchange()); the mode's state lives in shared memory (sm.misc + SIM_PP_*), not in registers
@@ -527,7 +526,6 @@ struct SimWarp {
         }
         __syncwarp();
         q -= 1;
-        n_rot += 1;
 #ifdef MPC_SIMT_EMULATION
         if (lane == 0) g_sim_rotations += nrot;
 #endif
@@ -541,9 +539,11 @@ struct SimWarp {
             if (fl) remove_at(a);
         }
     }
-    // Dual active-set QP, warm-started from the carried set AS IT IS.  (Shifting the set by one sample to follow the
-    // receding horizon was measured to cost more than it saves: the shifted guess sheds most of its members
-    // through negative multipliers and has to be rebuilt from W.)  z (registers) in: z_unc, out: optimum.
+    // Dual active-set QP, warm-started from the carried set as it is.  Shifting EVERY carried set by one sample to
+    // follow the receding horizon was measured to cost more than it saves; the shifted set is tried first only when
+    // most of the carried one comes back with negative multipliers (guided shifted restart below), and a run whose set
+    // alternates with period 2 re-enters the parked factor of the other phase (sim_pp_exchange).
+    // z (registers) in: z_unc, out: optimum.
     __device__ __forceinline__ int qp_solve() {
         int it = 0;
         const int itmax = 20 * (NU * m + 10);
@@ -874,7 +874,7 @@ __device__ __forceinline__ int sim_run(const MpcLayout &L, const MpcTables &T, i
         sm.chd = ip; ip += nch; sm.chj = ip; ip += nch; sm.role = ip; ip += nst;
         sm.act = ip; ip += R; sm.dflag = ip; ip += R; sm.misc = ip;
     }
-    wp.gscr = gscr; wp.W = Wg; wp.lane = lane; wp.m = m; wp.q = 0; wp.n_con = 0; wp.n_it = 0; wp.qmax = 0; wp.n_rot = 0; wp.churn = 0;
+    wp.gscr = gscr; wp.W = Wg; wp.lane = lane; wp.m = m; wp.q = 0; wp.n_con = 0; wp.n_it = 0; wp.qmax = 0; wp.churn = 0;
 #ifdef SIM_NO_TWO_PHASE
     wp.slot = nullptr;
 #else
