@@ -448,3 +448,31 @@ def test_nmpc_warp_per_run_variant(monkeypatch):
     v = ev.eval_batch(gold["N"][:2], gold["Nu"][:2], gold["delta"][:2], gold["lam"][:2], mode="vns")
     assert (np.abs(v["cost"] - gold["vns"]) / np.abs(gold["vns"])).max() < 5e-3
     ev.close()
+
+
+def test_two_phase_mode_on_limit_cycles(ev3, monkeypatch):
+    """The short-horizon family (N = 7..9) of the 32768-candidate population limit-cycles with period 2; k_sim re-enters
+    the parked factor of the other phase.  Same costs as the oracle and as the kernel with the
+    mode switched off, and several times fewer active-set iterations."""
+    p = ev3.prob
+    op = orc.OracleProblem(p)
+    Ng, Nug, dlg, lmg = synthetic_population(p, 32768, seed=0)
+    idx = np.array([4169, 12612, 26241, 31292, 11416, 26303])
+    N, Nu, dl, lm = Ng[idx], Nug[idx], dlg[idx], lmg[idx]
+    assert (N <= 9).all()
+    g0, st0, _ = orc.eval_batch(op, N, Nu, dl, lm, "gam")
+    its = {}
+    cost = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("MPCGPU_TWO_PHASE", flag)
+        c0 = ev3.counters()
+        out = ev3.eval_batch(N, Nu, dl, lm, mode="gam")
+        c1 = ev3.counters()
+        assert (out["status"] == 0).all()
+        its[flag] = c1["as_iterations"] - c0["as_iterations"]
+        cost[flag] = out["cost"]
+    assert its["1"] * 3 < its["0"], its
+    sens = oracle_sensitivity(op, N, Nu, dl, lm, "gam", g0)
+    check_cost(cost["1"], g0, sens, "shell3x3 limit cycles", min_strict=0.0)
+    check_cost(cost["0"], g0, sens, "shell3x3 limit cycles, mode off", min_strict=0.0)
+    check_cost(cost["1"], cost["0"], sens, "shell3x3 limit cycles, mode on vs off", min_strict=0.0)
