@@ -28,7 +28,7 @@
 #ifndef SIM_SHIFT_DEN
 #define SIM_SHIFT_DEN 2   /* guided shifted restart when more than 1/SIM_SHIFT_DEN of the carried multipliers are negative */
 #endif
-#define SIM_MISC_INTS 20  /* sm.misc: [2] scratch of the shifted restart, [3..18] state of the two-phase mode */
+#define SIM_MISC_INTS 22  /* sm.misc: [2] scratch of the shifted restart, [3..20] state of the two-phase mode */
 #define SIM_PP_ON 3
 #define SIM_PP_QS 9       /* [9], [10]: active-set sizes of the two parked factors */
 #define SIM_PP_CUR 4      /* slot that belongs to the carried factor */
@@ -41,6 +41,10 @@
 #define SIM_PP_BACK 17    /* back-off length after failed episodes */
 #define SIM_PP_WAIT 18    /* constrained-sample count before which the mode is not entered again */
 #define SIM_PP_GOOD 19    /* this episode had a cheap re-entry */
+#define SIM_PP_EVERGOOD 20 /* some episode of this run had one */
+#ifndef SIM_PP_AVG
+#define SIM_PP_AVG 6      /* mean iterations per constrained sample from which a run is eligible for the mode */
+#endif
 #define SIM_PP_SIG1 5
 #define SIM_PP_SIG2 6
 #define SIM_PP_COUNT 7   /* exchanges of this run (diagnostics) */
@@ -233,7 +237,7 @@ SIM_COLD int sim_pp_exchange(double *vli, int *act, int *misc, double *slot, int
 // End of a constrained solve that took `it` iterations and ended on `q` constraints: an expensive solve that ends on
 // the set of two samples ago, and not on the previous one, is a period-2 cycle -- start parking.  Leave the mode
 // again when a re-entered set turns out as expensive as a torn-down one.
-SIM_COLD void sim_pp_update(const int *act, int *misc, int lane, int q, int it, int QC, int ncon) {
+SIM_COLD void sim_pp_update(const int *act, int *misc, int lane, int q, int it, int QC, int ncon, int nit_run) {
     unsigned hsh = 0u;   // order-independent signature of the final active set
     for (int a = lane; a < q; a += 32) hsh ^= ((unsigned)act[a] + 1u) * 2654435761u;
     const int sig = (int)(__reduce_xor_sync(SIM_FULL, hsh) ^ ((unsigned)q << 26));
@@ -252,7 +256,7 @@ SIM_COLD void sim_pp_update(const int *act, int *misc, int lane, int q, int it, 
             if (reentered) {   // a re-entered set that is as expensive as a torn-down one: twice in a row, or very
                 const int bad = it >= SIM_PP_BADIT ? misc[SIM_PP_BAD] + 1 : 0;
                 misc[SIM_PP_BAD] = bad;
-                if (it <= SIM_PP_GOODIT) misc[SIM_PP_GOOD] = 1;
+                if (it <= SIM_PP_GOODIT) { misc[SIM_PP_GOOD] = 1; misc[SIM_PP_EVERGOOD] = 1; }
                 if (bad >= 2 || it >= 2 * SIM_PP_HEAVY) {
                     // leave; an episode without a single cheap re-entry was a false alarm: wait 16, 32, .. 256
                     // constrained samples before the next one
@@ -261,7 +265,10 @@ SIM_COLD void sim_pp_update(const int *act, int *misc, int lane, int q, int it, 
                     misc[SIM_PP_ON] = 0; misc[SIM_PP_BACK] = back; misc[SIM_PP_WAIT] = ncon + back;
                 }
             }
-        } else if (match && (match_prev || !SIM_PP_DOUBLE_MATCH) && ncon >= misc[SIM_PP_WAIT] && q <= QC && !SIM_KNOB(64)) {
+        } else if (match && (match_prev || !SIM_PP_DOUBLE_MATCH) && ncon >= misc[SIM_PP_WAIT] && q <= QC && !SIM_KNOB(64) &&
+                   (misc[SIM_PP_EVERGOOD] || nit_run >= SIM_PP_AVG * ncon)) {
+            // ... and only for a run that churns as a whole (SIM_PP_AVG iterations per constrained sample so far) or that
+            // the mode has already paid off for: moderately busy runs gain nothing and a chaotic one can lose
             misc[SIM_PP_ON] = 1; misc[SIM_PP_FIRST] = 1; misc[SIM_PP_CUR] = 0; misc[SIM_PP_DIRTY] = 1; misc[SIM_PP_BAD] = 0; misc[SIM_PP_GOOD] = 0;
         }
     }
@@ -753,7 +760,7 @@ struct SimWarp {
         SIM_DBGSET("final");
         // two-phase mode bookkeeping (cold, not inlined): only after an expensive solve or inside the mode -- called after
         // every constrained solve it cost all runs 4 % (gpurun_out/d28*.log)
-        if (slot && (it >= SIM_PP_HEAVY || sm.misc[SIM_PP_ON])) sim_pp_update(sm.act, sm.misc, lane, q, it, QC, (int)n_con);
+        if (slot && (it >= SIM_PP_HEAVY || sm.misc[SIM_PP_ON])) sim_pp_update(sm.act, sm.misc, lane, q, it, QC, (int)n_con, (int)n_it);
         return 0;
     }
 
