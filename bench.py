@@ -338,8 +338,8 @@ def main():
                          "hbm": {"algorithmic_bytes": hbm_alg, "achieved_gbs": hbm_alg / (sim_ms + build_ms) / 1e6,
                                  "peak_gbs": peaks.get("hbm_gbs"), "frac": (hbm_alg / (sim_ms + build_ms) / 1e6) / peaks["hbm_gbs"] if peaks.get("hbm_gbs") else None},
                          # dram__bytes_read.sum + dram__bytes_write.sum of the k_sim launch of one population,
-                         # ncu --set full capture profiles/r1j_k_sim_summary.json (same population, GAM mode)
-                         "traffic": 66.2e6 if (args.mode == "gam" and n == 4096) else None},
+                         # ncu --set full capture profiles/r1k_k_sim_summary.json (same population, GAM mode)
+                         "traffic": 65.2e6 if (args.mode == "gam" and n == 4096) else None},
             "counters": {k: cn[k] for k in ("qp_constrained", "as_iterations", "qp_solves", "closed_loops")},
             "failed_candidates": nfail,
         }
