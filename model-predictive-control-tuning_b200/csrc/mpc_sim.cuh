@@ -89,7 +89,11 @@ struct MpcRunOut {
 };
 
 static MPC_HD int sim_pad(int m) { return m <= 4 ? 4 : (m <= 8 ? 8 : 16); }
-static MPC_HD int sim_qc(int R) { return R <= 24 ? R : 24; }
+// active constraints whose factor rows live in shared memory; the rest spills to global memory
+#ifndef SIM_QC_MAX
+#define SIM_QC_MAX 24
+#endif
+static MPC_HD int sim_qc(int R) { return R <= SIM_QC_MAX ? R : SIM_QC_MAX; }
 // M (nst x R) lives in shared memory for the small buckets; for P = 16 it stays in global memory (read-only,
 // L1/L2 resident, loads independent of the state) so that twice as many runs fit on an SM.
 #ifndef SIM_M_GLOBAL_P
@@ -280,7 +284,7 @@ template <int NU, int P>
 struct SimWarp {
     static constexpr int R = NU * P;
     static constexpr int NSLOT = (R + 31) / 32;
-    static constexpr int QC = (R <= 24) ? R : 24;
+    static constexpr int QC = (R <= SIM_QC_MAX) ? R : SIM_QC_MAX;
 
     const MpcLayout &L;
     SimSm sm;
@@ -855,7 +859,7 @@ __device__ __forceinline__ int sim_run(const MpcLayout &L, const MpcTables &T, i
     if (LEAN) { out.y = nullptr; out.u = nullptr; out.ys = nullptr; out.uopt = nullptr; out.diag = nullptr; out.trace = nullptr; }
     constexpr int R = NU * P;
     constexpr int NSLOT = (R + 31) / 32;
-    constexpr int QC = (R <= 24) ? R : 24;
+    constexpr int QC = (R <= SIM_QC_MAX) ? R : SIM_QC_MAX;
     const int lane = threadIdx.x & 31;
     const int ny = L.ny, nd = L.nd, nw = L.nw, nch = ny * nw, nst = L.nst, nit = L.nit;
     const int HL = sim_hl(L);
