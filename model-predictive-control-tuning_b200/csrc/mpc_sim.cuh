@@ -850,13 +850,14 @@ struct SimWarp {
 // ------------------------------------------------------------------------------------------------
 // LEAN: the GAM cost-only specialisation (mode 1, no trajectories, no open-loop pass, no diagnostics) -- the image the
 // tuning loop and the benchmark run; dropping the other modes' code makes it ~20 % smaller (instruction cache).
-template <int NU, int P, bool LEAN = false>
+// VLEAN: the same for the VNS objective (mode 2: open-loop pass and lock-step open-loop rollout kept, no trajectories).
+template <int NU, int P, bool LEAN = false, bool VLEAN = false>
 __device__ __forceinline__ int sim_run(const MpcLayout &L, const MpcTables &T, int m, const double *__restrict__ Mg,
                                        const double *__restrict__ Wg, int mode_arg, int sel, double *smem, double *gscr,
                                        const MpcRunOut &out_arg, double *pslot = nullptr) {
-    const int mode = LEAN ? 1 : mode_arg;
+    const int mode = LEAN ? 1 : (VLEAN ? 2 : mode_arg);
     MpcRunOut out = out_arg;
-    if (LEAN) { out.y = nullptr; out.u = nullptr; out.ys = nullptr; out.uopt = nullptr; out.diag = nullptr; out.trace = nullptr; }
+    if (LEAN || VLEAN) { out.y = nullptr; out.u = nullptr; out.ys = nullptr; out.uopt = nullptr; out.diag = nullptr; out.trace = nullptr; }
     constexpr int R = NU * P;
     constexpr int NSLOT = (R + 31) / 32;
     constexpr int QC = (R <= SIM_QC_MAX) ? R : SIM_QC_MAX;
@@ -936,7 +937,7 @@ __device__ __forceinline__ int sim_run(const MpcLayout &L, const MpcTables &T, i
     __syncwarp();
     int head = 0;   // uniform: physical slot of lag 0 in every circular history
     int status = 0;
-    const bool want_ol = LEAN ? false : ((mode != 1) || out.ys || out.uopt);
+    const bool want_ol = LEAN ? false : (VLEAN ? true : ((mode != 1) || out.ys || out.uopt));
     double jnu = 0.0;
     double cost_acc = 0.0;  // per lane: lane i < ny accumulates output i
 

@@ -25,3 +25,13 @@ sim_kernel_t SIM_CAT(sim_lean_nu, SIM_NU)(int P) {
     }
     return nullptr;
 }
+
+// VNS cost-only specialisation (see sim_run)
+sim_kernel_t SIM_CAT(sim_vlean_nu, SIM_NU)(int P) {
+    switch (P) {
+        case 4: return k_sim<SIM_NU, 4, false, true>;
+        case 8: return k_sim<SIM_NU, 8, false, true>;
+        case 16: return k_sim<SIM_NU, 16, false, true>;
+    }
+    return nullptr;
+}

@@ -32,7 +32,7 @@ struct DevOut {
 
 
 // One warp per (candidate, run).  mode: 0 RAW, 1 GAM, 2 VNS.
-template <int NU, int P, bool LEAN = false>
+template <int NU, int P, bool LEAN = false, bool VLEAN = false>
 __global__ void __launch_bounds__(32) k_sim(const MpcLayout L, const MpcTables T, const int *order, int count, int runs,
                                             int mode, int square, long long item0, DevCand C, DevOut O) {
     extern __shared__ __align__(16) double smem_s[];
@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(32) k_sim(const MpcLayout L, const MpcTables T
     const int sel = mode == 2 ? (square ? run : -1) : -2;
     double *gscr = C.scratch ? C.scratch + (size_t)(item0 + item) * C.scratch_stride : nullptr;
     double *pslot = C.slot ? C.slot + (size_t)(item0 + item) * C.slot_stride : nullptr;
-    const int st = sim_run<NU, P, LEAN>(L, T, m, C.M + C.offM[c], C.W + C.offW[c], mode, sel, smem_s, gscr, out, pslot);
+    const int st = sim_run<NU, P, LEAN, VLEAN>(L, T, m, C.M + C.offM[c], C.W + C.offW[c], mode, sel, smem_s, gscr, out, pslot);
     if (st != 0 && (threadIdx.x & 31) == 0) atomicMax(O.status + c, st);
     if (out.diag && (threadIdx.x & 31) == 0) out.diag[3] = (unsigned long long)(clock64() - t_start);
 }
@@ -112,6 +112,10 @@ sim_kernel_t sim_lean_nu1(int P);
 sim_kernel_t sim_lean_nu2(int P);
 sim_kernel_t sim_lean_nu3(int P);
 sim_kernel_t sim_lean_nu4(int P);
+sim_kernel_t sim_vlean_nu1(int P);
+sim_kernel_t sim_vlean_nu2(int P);
+sim_kernel_t sim_vlean_nu3(int P);
+sim_kernel_t sim_vlean_nu4(int P);
 sim_kernel_t soft_kernel_nu1(int P);
 sim_kernel_t soft_kernel_nu2(int P);
 sim_kernel_t soft_kernel_nu3(int P);

@@ -69,6 +69,15 @@ static sim_kernel_t sim_lean(int nu, int P) {
     }
     return nullptr;
 }
+static sim_kernel_t sim_vlean(int nu, int P) {
+    switch (nu) {
+        case 1: return sim_vlean_nu1(P);
+        case 2: return sim_vlean_nu2(P);
+        case 3: return sim_vlean_nu3(P);
+        case 4: return sim_vlean_nu4(P);
+    }
+    return nullptr;
+}
 static sim_kernel_t sim_kernel(int nu, int P) {
     switch (nu) {
         case 1: return sim_kernel_nu1(P);
@@ -253,6 +262,7 @@ extern "C" int mpcgpu_create(const mpcgpu_problem *problem, int device, mpcgpu_h
     for (int P = 4; P <= 16; P *= 2) {
         cudaFuncSetAttribute(sim_kernel(t.L.nu, P), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin);
         cudaFuncSetAttribute(sim_lean(t.L.nu, P), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin);
+        cudaFuncSetAttribute(sim_vlean(t.L.nu, P), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin);
         cudaFuncSetAttribute(soft_kernel(t.L.nu, P), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin);
     }
     // check the largest footprints fit
@@ -481,7 +491,8 @@ extern "C" int mpcgpu_run(mpcgpu_handle *h, int cost_mode, int want_traj, void *
         } else {
             const size_t smem = sim_smem_doubles(L, nu, bk.P) * sizeof(double);
             const bool lean = cost_mode == MPCGPU_COST_GAM && !want_traj && !h->want_diag;   // the tuning loop's call
-            (lean ? sim_lean(nu, bk.P) : sim_kernel(nu, bk.P))<<<grid, 32, smem, h->pool[b % NSTREAM]>>>(L, T, h->dOrder.p + bk.off, bk.count, runs, cost_mode,
+            const bool vlean = cost_mode == MPCGPU_COST_VNS && !want_traj && !h->want_diag;   // ... and its VNS phase
+            (lean ? sim_lean(nu, bk.P) : (vlean ? sim_vlean(nu, bk.P) : sim_kernel(nu, bk.P)))<<<grid, 32, smem, h->pool[b % NSTREAM]>>>(L, T, h->dOrder.p + bk.off, bk.count, runs, cost_mode,
                                                                            square, item0, C, O);
         }
         CK(cudaGetLastError());
