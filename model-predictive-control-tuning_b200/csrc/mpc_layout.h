@@ -61,6 +61,7 @@ struct MpcTables {
     const double *ST;    // step responses of the MV channels s_ij(n): [(i*nu+j)*st_stride + n]
     const double *PA;    // channel pole powers a_ch^n: [ch*(pmax+1) + n]
     int st_stride;
+    const double *sig;   // the three signals packed sample-major: [k*(2ny+nd) + c], c = r (ny) | yref (ny) | v (nd)
 };
 
 static MPC_HD long long mpc_tg_index(const MpcLayout &L, int i, int D, int Lh, int j, int j2) {

@@ -61,9 +61,11 @@
 #define SIM_CHURN 24   /* iterations per constrained QP above which a run switches its pivot rule */
 #define SIM_REFRESH 96 /* Givens removals after which the factor of the soft-constraint kernel (mpc_soft.cuh) is refreshed */
 #ifndef SIM_MB
-#define SIM_MB 18 /* columns of M in flight per batch when M is read from global memory (P = 16) */
+#define SIM_MB 10 /* columns of M in flight per batch when M is read from global memory (P = 16); even */
 #endif
-#define SIM_CH 32 /* samples of r / yref / v staged into shared memory at a time */
+#ifndef SIM_CH
+#define SIM_CH 32 /* samples of r / yref / v staged into shared memory at a time (power of two) */
+#endif
 #define SIM_INF (__builtin_huge_val())
 #define SIM_FULL 0xffffffffu
 #ifdef MPC_SIMT_EMULATION   /* experiment switches, host emulation only */
@@ -94,6 +96,14 @@ static MPC_HD int sim_pad(int m) { return m <= 4 ? 4 : (m <= 8 ? 8 : 16); }
 #define SIM_QC_MAX 24
 #endif
 static MPC_HD int sim_qc(int R) { return R <= SIM_QC_MAX ? R : SIM_QC_MAX; }
+// the kernel without a spill area (mpc_sim_spec.cuh) keeps up to SIM_SPEC_QC factor rows, Li packed triangular
+#ifndef SIM_SPEC_QC
+#define SIM_SPEC_QC 32
+#endif
+static MPC_HD int sim_spec_qc(int R) { return R <= SIM_SPEC_QC ? R : SIM_SPEC_QC; }
+static MPC_HD size_t sim_spec_vli_doubles(int R) { const int qc = sim_spec_qc(R); return (size_t)qc * R + (size_t)qc * (qc + 1) / 2; }
+// per-run parking slots of the two-phase mode for that kernel
+static MPC_HD size_t sim_spec_slot_doubles(int R) { return 2 * (sim_spec_vli_doubles(R) + 32); }
 // M (nst x R) lives in shared memory for the small buckets; for P = 16 it stays in global memory (read-only,
 // L1/L2 resident, loads independent of the state) so that twice as many runs fit on an SM.
 #ifndef SIM_M_GLOBAL_P
@@ -127,7 +137,7 @@ static MPC_HD size_t sim_smem_doubles(const MpcLayout &L, int nu, int P) {
     n += (size_t)SIM_CH * (2 * L.ny + L.nd);  // sig
     n += (size_t)nu * P;                      // uopt
     n += 4 * nu;                              // bnd
-    n += 6 * (size_t)R;                       // z, lvl, w, wsc, w2, w2sc
+    n += 4 * (size_t)R;                       // z, lvl, w, wsc
     n += 4 * (size_t)R;                       // g, l, rr, mu
     n += (size_t)qc * R + (size_t)qc * qc;    // V, Li (full stride)
     n += (2 * nch + L.nst + 2 * R + SIM_MISC_INTS + 1) / 2 + 1;   // ints: chd, chj, role, act, dflag, misc
@@ -135,16 +145,24 @@ static MPC_HD size_t sim_smem_doubles(const MpcLayout &L, int nu, int P) {
 }
 
 struct SimSm {
-    double *M, *st, *x, *xol, *hist, *cha, *chb0, *chb1, *chg, *sig, *uopt, *bnd, *z, *lvl, *w, *wsc, *w2, *w2sc, *g, *l, *rr, *mu, *V, *Li;
+    double *M, *st, *x, *xol, *hist, *cha, *chb0, *chb1, *chg, *sig, *uopt, *bnd, *z, *lvl, *w, *wsc, *g, *l, *rr, *mu, *V, *Li;
     int *chd, *chj, *role, *act, *dflag, *misc;
 };
 
-__device__ __forceinline__ double sim_wsum(double v) {
+// The warp reductions and the segmented scan (-DSIM_OOL_REDUCE: out of line, 1100 SASS instructions less, but slower).
+#if defined(MPC_SIMT_EMULATION)
+#define SIM_OOL static inline
+#elif defined(SIM_OOL_REDUCE)
+#define SIM_OOL static __device__ __noinline__
+#else
+#define SIM_OOL static __device__ __forceinline__   /* measured: out of line costs 9 % (call latency, lost interleaving of the row slots) */
+#endif
+SIM_OOL double sim_wsum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(SIM_FULL, v, o);
     return v;
 }
-__device__ __forceinline__ double sim_wmax(double v) {
+SIM_OOL double sim_wmax(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(SIM_FULL, v, o));
     return v;
@@ -152,7 +170,8 @@ __device__ __forceinline__ double sim_wmax(double v) {
 // all lanes end with the minimum value and, among equal values, the smallest non-negative index.
 // Three warp-wide integer reductions (redux.sync) on an order-preserving 64-bit key instead of a five-step shuffle
 // butterfly on (double, int) pairs: this was the single hottest line of the active-set path (profiles/r1f).
-__device__ __forceinline__ void sim_wargmin(double &v, int &i) {
+struct SimArgMin { double v; int i; };
+SIM_OOL SimArgMin sim_wargmin_ool(double v, int i) {
     const unsigned long long b = (unsigned long long)__double_as_longlong(v);
     const unsigned long long key = (b >> 63) ? ~b : (b | 0x8000000000000000ull);   // unsigned order == numeric order
     const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
@@ -162,8 +181,24 @@ __device__ __forceinline__ void sim_wargmin(double &v, int &i) {
     const unsigned mi = __reduce_min_sync(SIM_FULL, (mine && i >= 0) ? (unsigned)i : 0xffffffffu);
     const unsigned long long mk = ((unsigned long long)mhi << 32) | mlo;
     const unsigned long long mb = (mk >> 63) ? (mk & 0x7fffffffffffffffull) : ~mk;
-    v = __longlong_as_double((long long)mb);
-    i = mi == 0xffffffffu ? -1 : (int)mi;
+    SimArgMin r;
+    r.v = __longlong_as_double((long long)mb);
+    r.i = mi == 0xffffffffu ? -1 : (int)mi;
+    return r;
+}
+__device__ __forceinline__ void sim_wargmin(double &v, int &i) {
+    const SimArgMin r = sim_wargmin_ool(v, i);
+    v = r.v; i = r.i;
+}
+// inclusive scan of v over the horizon index c inside each P-wide input segment
+template <int P>
+SIM_OOL double sim_segscan(double v, int c) {
+#pragma unroll
+    for (int off = 1; off < P; off <<= 1) {
+        const double t = __shfl_up_sync(SIM_FULL, v, off, P);
+        if (c >= off) v += t;
+    }
+    return v;
 }
 
 template <int NU>
@@ -193,15 +228,17 @@ __device__ __forceinline__ double sim_pick(const double (&u)[NU], int j) {
 // its slot only if the last solve changed it (in a settled cycle both factors are read-only: loads that stay in L2,
 // no stores to evict the M tables of the neighbouring runs).  Returns the new active-set size in bits [0,8) and this
 // lane's constraint masks (4 bits per row slot) from bit 8.
-SIM_COLD int sim_pp_exchange(double *vli, int *act, int *misc, double *slot, int lane, int q, int masks, int R, int QC) {
-    const size_t S = (size_t)QC * R + (size_t)QC * QC + 32;   // doubles per slot (the int part: QC + 32 ints <= 32 doubles)
+SIM_COLD int sim_pp_exchange(double *vli, int *act, int *misc, double *slot, int lane, int q, int masks, int R, int QC, int packed) {
+    // Li: QC x QC full stride, or packed lower triangular (rows [0,q) are the first q(q+1)/2 doubles)
+    const size_t LS = packed ? (size_t)QC * (QC + 1) / 2 : (size_t)QC * QC;
+    const size_t S = (size_t)QC * R + LS + 32;   // doubles per slot (the int part: QC + 32 ints <= 32 doubles)
     const int cur = misc[SIM_PP_CUR], dirty = misc[SIM_PP_DIRTY];
     double *sc = slot + (size_t)cur * S, *so = slot + (size_t)(1 - cur) * S;
-    int *ic = (int *)(sc + (size_t)QC * R + (size_t)QC * QC), *io = (int *)(so + (size_t)QC * R + (size_t)QC * QC);
+    int *ic = (int *)(sc + (size_t)QC * R + LS), *io = (int *)(so + (size_t)QC * R + LS);
     const int first = misc[SIM_PP_FIRST];   // first sample of the mode: park the carried factor, keep it as the warm start
     const int qb = first ? 0 : misc[SIM_PP_QS + 1 - cur];
     if (dirty) {
-        const int nv = q * R, n = q * (R + QC);
+        const int nv = q * R, n = nv + (packed ? q * (q + 1) / 2 : q * QC);
 #pragma unroll 1
         for (int j = lane; j < n; j += 32) {
             const int idx = j < nv ? j : QC * R + (j - nv);
@@ -213,7 +250,7 @@ SIM_COLD int sim_pp_exchange(double *vli, int *act, int *misc, double *slot, int
     __syncwarp();
     {   // rows [0, qb) of V and of Li as ONE loop over a virtual index, four independent global loads in flight per
         // pass (a dependent load per element made the re-entry cost ten active-set iterations)
-        const int nv = qb * R, n = qb * (R + QC);
+        const int nv = qb * R, n = nv + (packed ? qb * (qb + 1) / 2 : qb * QC);
 #pragma unroll 1
         for (int j0 = lane; j0 < n; j0 += 128) {
             double g[4];
@@ -279,12 +316,70 @@ SIM_COLD void sim_pp_update(const int *act, int *misc, int lane, int q, int it, 
     __syncwarp();
 }
 
+// Removal of the active constraint at position a (see SimWarp::remove_at) for the kernel WITHOUT a spill area
+// (every factor row in shared memory, q <= QC <= 32): one out-of-line copy shared by both call sites -- the closed-loop
+// kernel is bound by instruction fetch, the routine is ~500 SASS instructions when inlined.
+template <int R, int QC, int NSLOT>   // Li packed lower triangular: row i starts at i (i + 1) / 2
+SIM_COLD void sim_remove_nospill(double *V, double *Li, int *act, double *mu, double *g, double *rr, int lane, int a, int q) {
+    static_assert(QC <= 32, "one row slot of Li columns");
+    const int nrot = q - 1 - a;
+    if (nrot > 0) {
+        for (int t = lane; t < nrot; t += 32) {
+            double ss = 0.0;
+            for (int i = a; i <= a + t; ++i) { const double v = Li[i * (i + 1) / 2 + a]; ss = fma(v, v, ss); }
+            const double y = Li[(a + t + 1) * (a + t + 2) / 2 + a];
+            const double inv = 1.0 / sqrt(fma(y, y, ss));
+            g[t] = sqrt(ss) * inv;
+            rr[t] = y * inv;
+        }
+        __syncwarp();
+        double cv[NSLOT], cy0 = 0.0;
+        const int j0 = lane;
+#pragma unroll
+        for (int s = 0; s < NSLOT; ++s) cv[s] = lane + 32 * s < R ? V[(size_t)a * R + lane + 32 * s] : 0.0;
+        if (j0 < a) cy0 = Li[a * (a + 1) / 2 + j0];
+#pragma unroll 1
+        for (int t = 0; t < nrot; ++t) {
+            const int k = a + t;
+            const double cx = g[t], sy = rr[t];
+            __syncwarp();   // row k was read by the previous step
+            const double *vsrc = V + (size_t)(k + 1) * R;
+            double *vdst = V + (size_t)k * R;
+#pragma unroll
+            for (int s = 0; s < NSLOT; ++s)
+                if (lane + 32 * s < R) {
+                    const double o = vsrc[lane + 32 * s];
+                    vdst[lane + 32 * s] = cx * o - sy * cv[s];
+                    cv[s] = cx * cv[s] + sy * o;
+                }
+            const double *ysrc = Li + (k + 1) * (k + 2) / 2;
+            double *ydst = Li + k * (k + 1) / 2;
+            if (j0 != a && j0 <= k + 1) {
+                const double o = ysrc[j0];
+                ydst[j0 < a ? j0 : j0 - 1] = cx * o - sy * cy0;
+                cy0 = cx * cy0 + sy * o;
+            }
+        }
+        __syncwarp();
+        const int pos = a + 1 + lane;
+        const int ca = pos < q ? act[pos] : 0;
+        const double cm = pos < q ? mu[pos] : 0.0;
+        __syncwarp();
+        if (pos < q) { act[pos - 1] = ca; mu[pos - 1] = cm; }
+    }
+    __syncwarp();
+}
+
 // Everything one warp needs to carry through the run; template so that R, P, NSLOT are constants.
-template <int NU, int P>
+// SPILL: factor rows beyond QC live in a per-run global scratch; without it a QP that needs more than QC active
+// constraints returns status SIM_ST_OVERFLOW and the host re-runs the candidate on the kernel with the spill area.
+#define SIM_ST_OVERFLOW 6
+template <int NU, int P, bool SPILL = true>
 struct SimWarp {
     static constexpr int R = NU * P;
     static constexpr int NSLOT = (R + 31) / 32;
-    static constexpr int QC = (R <= SIM_QC_MAX) ? R : SIM_QC_MAX;
+    static constexpr int QCMAX = SPILL ? SIM_QC_MAX : SIM_SPEC_QC;
+    static constexpr int QC = (R <= QCMAX) ? R : QCMAX;
 
     const MpcLayout &L;
     SimSm sm;
@@ -309,9 +404,10 @@ struct SimWarp {
 
     __device__ __forceinline__ SimWarp(const MpcLayout &L_) : L(L_) {}
 
-    __device__ __forceinline__ double *Vcol(int a) const { return a < QC ? sm.V + (size_t)a * R : gscr + (size_t)(a - QC) * R; }
+    __device__ __forceinline__ double *Vcol(int a) const { return (!SPILL || a < QC) ? sm.V + (size_t)a * R : gscr + (size_t)(a - QC) * R; }
     // row a of the inverse Cholesky factor: entries [0..a]; QC doubles long in shared memory, R in the spill
     __device__ __forceinline__ double *Lirow(int a) const {
+        if (!SPILL) return sm.Li + a * (a + 1) / 2;   // packed lower triangular
         return a < QC ? sm.Li + (size_t)a * QC : gscr + (size_t)(R - QC) * R + (size_t)(a - QC) * R;
     }
 
@@ -319,15 +415,27 @@ struct SimWarp {
     __device__ __forceinline__ void levels(double (&lv)[NSLOT]) const {
 #pragma unroll
         for (int s = 0; s < NSLOT; ++s) {
-            double v = z[s];
-            const int c = row[s] & (P - 1);
-#pragma unroll
-            for (int off = 1; off < P; off <<= 1) {
-                const double t = __shfl_up_sync(SIM_FULL, v, off, P);
-                if (c >= off) v += t;
-            }
+            const double v = sim_segscan<P>(z[s], row[s] & (P - 1));
             lv[s] = sim_pick<NU>(u, (row[s] / P) < NU ? (row[s] / P) : 0) + v;
         }
+    }
+    // the same for any plan zz and MV levels uu (block verification of mpc_sim_spec.cuh)
+    __device__ __forceinline__ void levels_of(const double (&zz)[NSLOT], const double (&uu)[NU], double (&lv)[NSLOT]) const {
+#pragma unroll
+        for (int s = 0; s < NSLOT; ++s) {
+            const double v = sim_segscan<P>(zz[s], row[s] & (P - 1));
+            lv[s] = sim_pick<NU>(uu, (row[s] / P) < NU ? (row[s] / P) : 0) + v;
+        }
+    }
+    // does the plan zz with levels lv violate a rate or level limit on this lane's rows?
+    __device__ __forceinline__ int infeasible(const double (&zz)[NSLOT], const double (&lv)[NSLOT]) const {
+        int bad = 0;
+#pragma unroll
+        for (int s = 0; s < NSLOT; ++s)
+            if (valid[s])
+                bad |= (zz[s] - dlo[s] < -SIM_VIOL_TOL) | (dhi[s] - zz[s] < -SIM_VIOL_TOL) |
+                       (lv[s] - ulo[s] < -SIM_VIOL_TOL) | (uhi[s] - lv[s] < -SIM_VIOL_TOL);
+        return bad;
     }
     __device__ __forceinline__ void publish(const double (&lv)[NSLOT]) const {
 #pragma unroll
@@ -363,13 +471,7 @@ struct SimWarp {
         for (int s = 0; s < NSLOT; ++s) wv[s] = row[s] < R ? sg * src[row[s]] : 0.0;
 #pragma unroll
         for (int s = 0; s < NSLOT; ++s) {
-            double v = wv[s];
-            const int c = row[s] & (P - 1);
-#pragma unroll
-            for (int off = 1; off < P; off <<= 1) {
-                const double t = __shfl_up_sync(SIM_FULL, v, off, P);
-                if (c >= off) v += t;
-            }
+            const double v = sim_segscan<P>(wv[s], row[s] & (P - 1));
             if (row[s] < R) { dst[row[s]] = wv[s]; dsts[row[s]] = v; }
         }
         __syncwarp();
@@ -407,11 +509,13 @@ struct SimWarp {
             double a0 = 0.0, a1 = 0.0;
             int b = a;
 #pragma unroll 1
-            for (; b + 1 < qs; b += 2) { a0 = fma(sm.Li[(size_t)b * QC + a], sm.l[b], a0); a1 = fma(sm.Li[(size_t)(b + 1) * QC + a], sm.l[b + 1], a1); }
-            if (b < qs) { a0 = fma(sm.Li[(size_t)b * QC + a], sm.l[b], a0); ++b; }
+            for (; b + 1 < qs; b += 2) { a0 = fma(Lirow(b)[a], sm.l[b], a0); a1 = fma(Lirow(b + 1)[a], sm.l[b + 1], a1); }
+            if (b < qs) { a0 = fma(Lirow(b)[a], sm.l[b], a0); ++b; }
             if (b < QC) b = QC;
+            if (SPILL) {
 #pragma unroll 1
-            for (; b < qq; ++b) a0 = fma(Lirow(b)[a], sm.l[b], a0);   // spilled rows (rare)
+                for (; b < qq; ++b) a0 = fma(Lirow(b)[a], sm.l[b], a0);   // spilled rows (rare)
+            }
             out[a] = a0 + a1;
         }
         __syncwarp();
@@ -434,13 +538,15 @@ struct SimWarp {
             for (int s = 0; s < NSLOT; ++s)
                 if (row[s] < R) acc[s] = fma(ca, sm.V[(size_t)a * R + row[s]], acc[s]);
         }
+        if (SPILL) {
 #pragma unroll 1
-        for (int a = QC; a < qq; ++a) {   // spilled columns (rare)
-            const double ca = coef[a];
-            const double *va = Vcol(a);
+            for (int a = QC; a < qq; ++a) {   // spilled columns (rare)
+                const double ca = coef[a];
+                const double *va = Vcol(a);
 #pragma unroll
-            for (int s = 0; s < NSLOT; ++s)
-                if (row[s] < R) acc[s] = fma(ca, va[row[s]], acc[s]);
+                for (int s = 0; s < NSLOT; ++s)
+                    if (row[s] < R) acc[s] = fma(ca, va[row[s]], acc[s]);
+            }
         }
 #pragma unroll
         for (int s = 0; s < NSLOT; ++s) x[s] += sign * acc[s];
@@ -473,6 +579,14 @@ struct SimWarp {
 #pragma unroll
         for (int s = 0; s < NSLOT; ++s)
             if (row[s] == (cid >> 2)) amask[s] &= ~(1 << (cid & 3));
+        if (!SPILL) {
+            sim_remove_nospill<R, QC, NSLOT>(sm.V, sm.Li, sm.act, sm.mu, sm.g, sm.rr, lane, a, q);
+            q -= 1;
+#ifdef MPC_SIMT_EMULATION
+            if (lane == 0) g_sim_rotations += nrot;
+#endif
+            return;
+        }
         if (nrot > 0) {
             // rotation coefficients (cx, cy) = (x, y) / hypot(x, y), kept in sm.g / sm.rr
             for (int t = lane; t < nrot; t += 32) {
@@ -578,7 +692,7 @@ struct SimWarp {
                 int masks = 0;
 #pragma unroll
                 for (int s = 0; s < NSLOT; ++s) masks |= amask[s] << (4 * s);
-                const int r_ = sim_pp_exchange(sm.V, sm.act, sm.misc, slot, lane, q, masks, R, QC);
+                const int r_ = sim_pp_exchange(sm.V, sm.act, sm.misc, slot, lane, q, masks, R, QC, SPILL ? 0 : 1);
                 q = r_ & 255;
 #pragma unroll
                 for (int s = 0; s < NSLOT; ++s) amask[s] = (r_ >> (8 + 4 * s)) & 15;
@@ -613,6 +727,7 @@ struct SimWarp {
                     nneg += __popc(__ballot_sync(SIM_FULL, fl));
                 }
                 nd_ = nneg > 0;
+                #ifndef SIM_NO_SHIFT
                 if (first_pass && SIM_SHIFT_DEN * nneg > q && !SIM_KNOB(32)) {
                     // Most of the carried set has the wrong sign: the plan is one that moves along the horizon
                     // (alternating rate limits of an aggressive tuning shift by one index per sample).  Forget the
@@ -635,6 +750,7 @@ struct SimWarp {
                     it += 1;
                     break;
                 }
+#endif
             }
             first_pass = false;
             nd_ = __any_sync(SIM_FULL, nd_);
@@ -734,6 +850,7 @@ struct SimWarp {
                 __syncwarp();
                 if (!full) SIM_DBG("    partial step t=%.3e drop pos %d (%c%d.%d) dependent=%d\n", t, l1, "dDuU"[sm.act[l1 < 0 ? 0 : l1] & 3], (sm.act[l1 < 0 ? 0 : l1] >> 2) / P, (sm.act[l1 < 0 ? 0 : l1] >> 2) % P, dependent);
                 if (full) {
+                    if (!SPILL && q >= QC) { n_it += it; return SIM_ST_OVERFLOW; }   // re-run on the kernel with the spill area
                     commit(p, q, rho, mu_p, dir);
                     q += 1;
                     break;
@@ -798,31 +915,26 @@ struct SimWarp {
 #pragma unroll
             for (int s = 0; s < NSLOT; ++s) z[s] = acc0[s] + acc1[s];
         } else {
-            // M from global memory: SIM_MB columns (SIM_MB * NSLOT independent loads per lane) in flight at a time
+            // M from global memory: SIM_MB columns (SIM_MB * NSLOT independent loads per lane) in flight at a time; the last
+            // batch is predicated, not a column-at-a-time tail (each of those was a dependent L2 round trip)
             double acc0[NSLOT], acc1[NSLOT];
 #pragma unroll
             for (int s = 0; s < NSLOT; ++s) { acc0[s] = 0.0; acc1[s] = 0.0; }
             const double *mp = Mp + lane;
-            int sg = 0;
-            for (; sg + SIM_MB <= nst; sg += SIM_MB) {
+#pragma unroll 1
+            for (int sg = 0; sg < nst; sg += SIM_MB) {
                 double mv[SIM_MB][NSLOT];
 #pragma unroll
                 for (int e = 0; e < SIM_MB; ++e)
 #pragma unroll
                     for (int s = 0; s < NSLOT; ++s)
-                        mv[e][s] = valid[s] ? __ldg(mp + (size_t)(sg + e) * R + s * 32) : 0.0;   // padded rows of M are zero: not fetched
+                        mv[e][s] = (valid[s] && sg + e < nst) ? __ldg(mp + (size_t)(sg + e) * R + s * 32) : 0.0;   // padded rows of M are zero: not fetched
 #pragma unroll
                 for (int e = 0; e < SIM_MB; e += 2) {
-                    const double s0 = sm.st[sg + e], s1 = sm.st[sg + e + 1];
+                    const double s0 = sg + e < nst ? sm.st[sg + e] : 0.0, s1 = sg + e + 1 < nst ? sm.st[sg + e + 1] : 0.0;
 #pragma unroll
                     for (int s = 0; s < NSLOT; ++s) { acc0[s] = fma(mv[e][s], s0, acc0[s]); acc1[s] = fma(mv[e + 1][s], s1, acc1[s]); }
                 }
-            }
-            for (; sg < nst; ++sg) {
-                const double s0 = sm.st[sg];
-#pragma unroll
-                for (int s = 0; s < NSLOT; ++s)
-                    if (valid[s]) acc0[s] = fma(__ldg(mp + (size_t)sg * R + s * 32), s0, acc0[s]);
             }
 #pragma unroll
             for (int s = 0; s < NSLOT; ++s) z[s] = acc0[s] + acc1[s];
@@ -878,7 +990,7 @@ __device__ __forceinline__ int sim_run(const MpcLayout &L, const MpcTables &T, i
         sm.sig = p; p += (size_t)SIM_CH * nsig;
         sm.uopt = p; p += NU * P;
         sm.bnd = p; p += 4 * NU;
-        sm.z = p; p += R; sm.lvl = p; p += R; sm.w = p; p += R; sm.wsc = p; p += R; sm.w2 = p; p += R; sm.w2sc = p; p += R;
+        sm.z = p; p += R; sm.lvl = p; p += R; sm.w = p; p += R; sm.wsc = p; p += R;
         sm.g = p; p += R; sm.l = p; p += R; sm.rr = p; p += R; sm.mu = p; p += R;
         sm.V = p; p += (size_t)QC * R;
         sm.Li = p; p += (size_t)QC * QC;

@@ -35,3 +35,13 @@ sim_kernel_t SIM_CAT(sim_vlean_nu, SIM_NU)(int P) {
     }
     return nullptr;
 }
+
+// speculative kernel (mpc_sim_spec.cuh): the single P = 16 image, full / GAM cost-only / VNS cost-only
+sim_kernel_t SIM_CAT(sim_spec_nu, SIM_NU)(int variant) {
+    switch (variant) {
+        case 0: return k_sim<SIM_NU, 16, false, false, true>;
+        case 1: return k_sim<SIM_NU, 16, true, false, true>;
+        case 2: return k_sim<SIM_NU, 16, false, true, true>;
+    }
+    return nullptr;
+}

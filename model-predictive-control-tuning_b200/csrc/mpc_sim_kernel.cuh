@@ -7,6 +7,7 @@
 
 #include "../../include/mpcgpu.h"
 #include "mpc_sim.cuh"
+#include "mpc_sim_spec.cuh"
 #include "mpc_soft.cuh"
 
 struct DevCand {
@@ -25,6 +26,7 @@ struct DevOut {
     double *cost;   // GAM: n*ny ; VNS: n
     double *part;   // VNS partial sums n*runs
     int *status;    // n
+    int *status2;   // n: status of the re-run of candidates whose QP outgrew the speculative kernel's factor (SIM_ST_OVERFLOW)
     unsigned long long *counters;  // [0] constrained QPs [1] active-set iterations
     double *y, *u, *ys, *uopt;     // optional trajectories
     unsigned long long *diag;      // optional per-run diagnostics (4 per run)
@@ -32,8 +34,12 @@ struct DevOut {
 
 
 // One warp per (candidate, run).  mode: 0 RAW, 1 GAM, 2 VNS.
-template <int NU, int P, bool LEAN = false, bool VLEAN = false>
-__global__ void __launch_bounds__(32) k_sim(const MpcLayout L, const MpcTables T, const int *order, int count, int runs,
+// SPEC: lane-resident state + speculative unconstrained stretches (mpc_sim_spec.cuh; plants with nst <= 32).
+template <int NU, int P, bool LEAN = false, bool VLEAN = false, bool SPEC = false>
+#ifndef SIM_SPEC_MINB
+#define SIM_SPEC_MINB 12   /* resident runs per SM the speculative kernel's register budget is sized for */
+#endif
+__global__ void __launch_bounds__(32, SPEC ? SIM_SPEC_MINB : 1) k_sim(const MpcLayout L, const MpcTables T, const int *order, int count, int runs,
                                             int mode, int square, long long item0, DevCand C, DevOut O) {
     extern __shared__ __align__(16) double smem_s[];
     const int item = blockIdx.x;
@@ -42,9 +48,14 @@ __global__ void __launch_bounds__(32) k_sim(const MpcLayout L, const MpcTables T
     const int run = item - (item / runs) * runs;
     const int m = C.Nu[c];
     const int ny = L.ny, nit = L.nit;
+    // mode bit 8: second pass over the candidates the speculative kernel gave up on (more than QC active constraints)
+    const bool redo = (mode & 256) != 0;
+    mode &= 255;
+    if (redo && O.status[c] != SIM_ST_OVERFLOW) return;
+    int *stat = redo ? O.status2 : O.status;
     if (C.bstatus[c] != 0) {
         if ((threadIdx.x & 31) == 0) {
-            atomicMax(O.status + c, C.bstatus[c]);
+            atomicMax(stat + c, C.bstatus[c]);
             if (mode == 1) for (int i = 0; i < ny; ++i) O.cost[(size_t)c * ny + i] = NAN;
             if (mode == 2) O.part[(size_t)c * runs + run] = NAN;
         }
@@ -63,8 +74,9 @@ __global__ void __launch_bounds__(32) k_sim(const MpcLayout L, const MpcTables T
     const int sel = mode == 2 ? (square ? run : -1) : -2;
     double *gscr = C.scratch ? C.scratch + (size_t)(item0 + item) * C.scratch_stride : nullptr;
     double *pslot = C.slot ? C.slot + (size_t)(item0 + item) * C.slot_stride : nullptr;
-    const int st = sim_run<NU, P, LEAN, VLEAN>(L, T, m, C.M + C.offM[c], C.W + C.offW[c], mode, sel, smem_s, gscr, out, pslot);
-    if (st != 0 && (threadIdx.x & 31) == 0) atomicMax(O.status + c, st);
+    const int st = SPEC ? sim_run_spec<NU, P, LEAN, VLEAN>(L, T, m, C.M + C.offM[c], C.W + C.offW[c], mode, sel, smem_s, gscr, out, pslot)
+                        : sim_run<NU, P, LEAN, VLEAN>(L, T, m, C.M + C.offM[c], C.W + C.offW[c], mode, sel, smem_s, gscr, out, pslot);
+    if (st != 0 && (threadIdx.x & 31) == 0) atomicMax(stat + c, st);
     if (out.diag && (threadIdx.x & 31) == 0) out.diag[3] = (unsigned long long)(clock64() - t_start);
 }
 
@@ -116,6 +128,10 @@ sim_kernel_t sim_vlean_nu1(int P);
 sim_kernel_t sim_vlean_nu2(int P);
 sim_kernel_t sim_vlean_nu3(int P);
 sim_kernel_t sim_vlean_nu4(int P);
+sim_kernel_t sim_spec_nu1(int variant);   // variant 0 full, 1 GAM cost-only, 2 VNS cost-only; P = 16 image only
+sim_kernel_t sim_spec_nu2(int variant);
+sim_kernel_t sim_spec_nu3(int variant);
+sim_kernel_t sim_spec_nu4(int variant);
 sim_kernel_t soft_kernel_nu1(int P);
 sim_kernel_t soft_kernel_nu2(int P);
 sim_kernel_t soft_kernel_nu3(int P);

@@ -24,6 +24,15 @@ std::string mpc_set_signals(MpcHostTables &t, int nit, const double *r, const do
     t.r.assign(r, r + (size_t)nit * L.ny);
     if (L.nd > 0) t.v.assign(v, v + (size_t)nit * L.nd); else t.v.assign(1, 0.0);
     if (yref) t.yref.assign(yref, yref + (size_t)nit * L.ny); else t.yref.assign((size_t)nit * L.ny, 0.0);
+    const int nsg = 2 * L.ny + L.nd;
+    t.sig.assign((size_t)nit * nsg, 0.0);
+    for (int k = 0; k < nit; ++k) {
+        for (int i = 0; i < L.ny; ++i) {
+            t.sig[(size_t)k * nsg + i] = t.r[(size_t)k * L.ny + i];
+            t.sig[(size_t)k * nsg + L.ny + i] = t.yref[(size_t)i * nit + k];
+        }
+        for (int d = 0; d < L.nd; ++d) t.sig[(size_t)k * nsg + 2 * L.ny + d] = t.v[(size_t)k * L.nd + d];
+    }
     return "";
 }
 

@@ -12,6 +12,7 @@ struct MpcHostTables {
     std::vector<double> step;  // s_ij(n), [i][j][n], n = 0..pmax+mmax+1 (stride pmax+mmax+2)
     std::vector<double> pa;    // a_ch^n, [ch][n], n = 0..pmax
     std::vector<double> r, v, yref;
+    std::vector<double> sig;   // r | yref | v packed sample-major (nit x (2ny+nd)): what the closed-loop kernel stages
     std::vector<int> dmin;
 };
 

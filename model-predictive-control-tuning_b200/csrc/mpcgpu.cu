@@ -78,6 +78,15 @@ static sim_kernel_t sim_vlean(int nu, int P) {
     }
     return nullptr;
 }
+static sim_kernel_t sim_spec(int nu, int variant) {
+    switch (nu) {
+        case 1: return sim_spec_nu1(variant);
+        case 2: return sim_spec_nu2(variant);
+        case 3: return sim_spec_nu3(variant);
+        case 4: return sim_spec_nu4(variant);
+    }
+    return nullptr;
+}
 static sim_kernel_t sim_kernel(int nu, int P) {
     switch (nu) {
         case 1: return sim_kernel_nu1(P);
@@ -94,6 +103,12 @@ __global__ void k_finish_vns(int n, int runs, const int *N, const double *part, 
     double acc = 0.0;
     for (int r = 0; r < runs; ++r) acc += part[(size_t)c * runs + r];  // fixed order: deterministic
     cost[c] = status[c] ? NAN : acc + (double)N[c];
+}
+
+// candidates re-run on the kernel with the spill area take the status of that run
+__global__ void k_merge_status(int n, int *status, const int *status2) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < n && status[c] == SIM_ST_OVERFLOW) status[c] = status2[c];
 }
 
 __global__ void k_mark_invalid(int n, const int *invalid, int ny, int mode, int *status, double *cost) {
@@ -154,7 +169,7 @@ struct mpcgpu_handle {
     cudaStream_t stream = nullptr;          // own stream for eval_batch / upload / download
     cudaStream_t pool[NSTREAM] = {};
     cudaEvent_t ev_fork = nullptr, ev_join[NSTREAM] = {}, ev_t0 = nullptr, ev_t1 = nullptr, ev_t2 = nullptr;
-    DBuf<double> dTG, dTK, dS1, dR, dV, dYref, dST, dPA;
+    DBuf<double> dTG, dTK, dS1, dR, dV, dYref, dST, dPA, dSig;
     // population
     int n = 0;
     bool uploaded = false, ran = false;
@@ -164,7 +179,7 @@ struct mpcgpu_handle {
     struct Bucket { int P, mmax, off, count; };
     std::vector<Bucket> buckets;
     int n_valid = 0;
-    DBuf<int> dN, dNu, dOrder, dInvalid, dBStatus, dStatus;
+    DBuf<int> dN, dNu, dOrder, dInvalid, dBStatus, dStatus, dStatus2;
     DBuf<long long> dOffM, dOffW;
     DBuf<double> dDelta, dLambda, dM, dW, dCost, dPart, dY, dU, dYs, dUopt, dScratch;
     DBuf<unsigned long long> dCounters, dDiag;
@@ -174,12 +189,14 @@ struct mpcgpu_handle {
     HBuf<int> pinI;
     mpcgpu_counters cnt = {};
     size_t smem_optin = 0;
+    int sm_count = 148;
 };
 
 static MpcTables dev_tables(mpcgpu_handle *h) {
     MpcTables T;
     T.TG = h->dTG.p; T.TK = h->dTK.p; T.S1 = h->dS1.p; T.r = h->dR.p; T.v = h->dV.p; T.yref = h->dYref.p;
     T.ST = h->dST.p; T.PA = h->dPA.p; T.st_stride = h->ht.L.pmax + h->ht.L.mmax + 2;
+    T.sig = h->dSig.p;
     return T;
 }
 
@@ -188,6 +205,8 @@ static int upload_signals(mpcgpu_handle *h) {
     CK(h->dR.ensure(t.r.size()));
     CK(h->dV.ensure(t.v.size()));
     CK(h->dYref.ensure(t.yref.size()));
+    CK(h->dSig.ensure(t.sig.size()));
+    CK(cudaMemcpyAsync(h->dSig.p, t.sig.data(), t.sig.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->dR.p, t.r.data(), t.r.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->dV.p, t.v.data(), t.v.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->dYref.p, t.yref.data(), t.yref.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
@@ -232,6 +251,7 @@ extern "C" int mpcgpu_create(const mpcgpu_problem *problem, int device, mpcgpu_h
         return MPCGPU_ERR_CUDA;
     }
     h->smem_optin = prop.sharedMemPerBlockOptin;
+    h->sm_count = prop.multiProcessorCount;
     if ((ce = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("stream", ce);
     for (int i = 0; i < NSTREAM; ++i) {
         if ((ce = cudaStreamCreateWithFlags(&h->pool[i], cudaStreamNonBlocking)) != cudaSuccess) return fail("stream", ce);
@@ -265,9 +285,12 @@ extern "C" int mpcgpu_create(const mpcgpu_problem *problem, int device, mpcgpu_h
         cudaFuncSetAttribute(sim_vlean(t.L.nu, P), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin);
         cudaFuncSetAttribute(soft_kernel(t.L.nu, P), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin);
     }
+    for (int v = 0; v < 3; ++v)
+        if ((ce = cudaFuncSetAttribute(sim_spec(t.L.nu, v), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin)) != cudaSuccess)
+            return fail("cudaFuncSetAttribute(k_sim spec)", ce);
     // check the largest footprints fit
     const size_t sb = mpc_builder_smem_doubles(t.L.nu * t.L.mmax, t.L.nst) * sizeof(double);
-    const size_t ss = sim_smem_doubles(t.L, t.L.nu, sim_pad(t.L.mmax)) * sizeof(double);
+    const size_t ss = (sim_spec_ok(t.L) ? sim_spec_smem_doubles(t.L, t.L.nu, 16) : sim_smem_doubles(t.L, t.L.nu, sim_pad(t.L.mmax))) * sizeof(double);
     if (sb > h->smem_optin - 1024 || ss > h->smem_optin) {
         g_create_error = "problem too large for shared memory (builder " + std::to_string(sb) + " B, sim " +
                          std::to_string(ss) + " B)";
@@ -291,9 +314,9 @@ extern "C" void mpcgpu_destroy(mpcgpu_handle *h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    h->dTG.release(); h->dTK.release(); h->dS1.release(); h->dST.release(); h->dPA.release(); h->dR.release(); h->dV.release(); h->dYref.release();
+    h->dTG.release(); h->dTK.release(); h->dS1.release(); h->dST.release(); h->dPA.release(); h->dR.release(); h->dV.release(); h->dYref.release(); h->dSig.release();
     h->dN.release(); h->dNu.release(); h->dOrder.release(); h->dInvalid.release(); h->dBStatus.release();
-    h->dStatus.release(); h->dOffM.release(); h->dOffW.release(); h->dDelta.release(); h->dLambda.release();
+    h->dStatus.release(); h->dStatus2.release(); h->dOffM.release(); h->dOffW.release(); h->dDelta.release(); h->dLambda.release();
     h->dM.release(); h->dW.release(); h->dCost.release(); h->dPart.release(); h->dY.release(); h->dU.release();
     h->dYs.release(); h->dUopt.release(); h->dCounters.release(); h->dScratch.release(); h->dDiag.release();
     h->pinD.release(); h->pinOut.release(); h->pinI.release();
@@ -373,7 +396,7 @@ extern "C" int mpcgpu_upload(mpcgpu_handle *h, int n, const int32_t *N, const in
     }
     const size_t nn = (size_t)(n > 0 ? n : 1);
     CK(h->dN.ensure(nn)); CK(h->dNu.ensure(nn)); CK(h->dOrder.ensure(nn)); CK(h->dInvalid.ensure(nn));
-    CK(h->dBStatus.ensure(nn)); CK(h->dStatus.ensure(nn)); CK(h->dOffM.ensure(nn)); CK(h->dOffW.ensure(nn));
+    CK(h->dBStatus.ensure(nn)); CK(h->dStatus.ensure(nn)); CK(h->dStatus2.ensure(nn)); CK(h->dOffM.ensure(nn)); CK(h->dOffW.ensure(nn));
     CK(h->dDelta.ensure(nn * ny)); CK(h->dLambda.ensure(nn * nu));
     CK(h->dM.ensure((size_t)offM + 1)); CK(h->dW.ensure((size_t)offW + 1));
     // stage through pinned memory: [delta | lambda] doubles, [N | Nu | order | invalid] ints, offsets
@@ -431,7 +454,7 @@ extern "C" int mpcgpu_run(mpcgpu_handle *h, int cost_mode, int want_traj, void *
         scr_items += (long long)bk.count * runs;
     }
     long long slot_stride = 0;
-    for (const auto &bk : h->buckets) slot_stride = std::max(slot_stride, (long long)sim_slot_doubles(nu * bk.P));
+    for (const auto &bk : h->buckets) slot_stride = std::max(slot_stride, (long long)std::max(sim_slot_doubles(nu * bk.P), sim_spec_slot_doubles(nu * bk.P)));
     // the block kernel of the soft-constraint path has no such mode; MPCGPU_TWO_PHASE=0 switches it off (A/B runs)
     const char *tp_env = getenv("MPCGPU_TWO_PHASE");
     const bool two_phase = !L.has_ov_bounds && !(tp_env && atoi(tp_env) == 0);
@@ -440,7 +463,7 @@ extern "C" int mpcgpu_run(mpcgpu_handle *h, int cost_mode, int want_traj, void *
     DevCand C{h->dN.p, h->dNu.p, h->dDelta.p, h->dLambda.p, h->dOffM.p, h->dOffW.p, h->dM.p, h->dW.p, h->dBStatus.p,
               scr_stride > 0 ? h->dScratch.p : nullptr, scr_stride,
               two_phase ? h->dScratch.p + scr_stride * scr_items : nullptr, slot_stride};
-    DevOut O{h->dCost.p, h->dPart.p, h->dStatus.p, h->dCounters.p,
+    DevOut O{h->dCost.p, h->dPart.p, h->dStatus.p, h->dStatus2.p, h->dCounters.p,
              want_traj ? h->dY.p : nullptr, want_traj ? h->dU.p : nullptr, want_traj ? h->dYs.p : nullptr,
              want_traj ? h->dUopt.p : nullptr, nullptr};
     if (h->want_diag) {
@@ -452,6 +475,7 @@ extern "C" int mpcgpu_run(mpcgpu_handle *h, int cost_mode, int want_traj, void *
     const MpcTables T = dev_tables(h);
     CK(cudaEventRecord(h->ev_t0, s));
     CK(cudaMemsetAsync(h->dStatus.p, 0, sizeof(int) * nn, s));
+    CK(cudaMemsetAsync(h->dStatus2.p, 0, sizeof(int) * nn, s));
     CK(cudaMemsetAsync(h->dCounters.p, 0, sizeof(unsigned long long) * 4, s));
     if (want_traj) {  // rows a run does not own (VNS on a square plant) and invalid candidates read as zero
         CK(cudaMemsetAsync(h->dY.p, 0, sizeof(double) * nn * ny * nit, s));
@@ -489,11 +513,32 @@ extern "C" int mpcgpu_run(mpcgpu_handle *h, int cost_mode, int want_traj, void *
             soft_kernel(nu, bk.P)<<<grid, SOFT_THREADS, smem, h->pool[b % NSTREAM]>>>(L, T, h->dOrder.p + bk.off, bk.count, runs,
                                                                                    cost_mode, square, item0, C, O);
         } else {
-            const size_t smem = sim_smem_doubles(L, nu, bk.P) * sizeof(double);
+            // plants whose deviation state fits one warp run the speculative kernel (MPCGPU_SPEC=0: the plain one, A/B runs)
+            static const bool spec_off = getenv("MPCGPU_SPEC") && atoi(getenv("MPCGPU_SPEC")) == 0;
+            const bool spec = sim_spec_ok(L) && bk.P == 16 && !spec_off;
             const bool lean = cost_mode == MPCGPU_COST_GAM && !want_traj && !h->want_diag;   // the tuning loop's call
-            const bool vlean = cost_mode == MPCGPU_COST_VNS && !want_traj && !h->want_diag;   // ... and its VNS phase
-            (lean ? sim_lean(nu, bk.P) : (vlean ? sim_vlean(nu, bk.P) : sim_kernel(nu, bk.P)))<<<grid, 32, smem, h->pool[b % NSTREAM]>>>(L, T, h->dOrder.p + bk.off, bk.count, runs, cost_mode,
+            size_t smem = (spec ? sim_spec_smem_doubles(L, nu, bk.P, lean) : sim_smem_doubles(L, nu, bk.P)) * sizeof(double);
+            {   // Resident runs per SM.  The kernel is bound by instruction fetch: co-resident runs slow
+                // each other down, so a SMALL population, whose step lasts as long as its heaviest run, finishes sooner with
+                // fewer runs per SM (measured on 4096 Shell3x3 candidates: 10.4 ms at 10 per SM, 9.1 ms at 5), while a large
+                // one wants them all (16384: 21.0 ms at 10, 30.7 ms at 5).  MPCGPU_RUNS_PER_SM overrides the choice.
+                static const int rps_env = getenv("MPCGPU_RUNS_PER_SM") ? atoi(getenv("MPCGPU_RUNS_PER_SM")) : 0;
+                const int rps = rps_env > 0 ? rps_env : ((long long)grid <= 40LL * h->sm_count ? 5 : 0);
+                if (rps > 0) { const size_t want = (size_t)(228 * 1024) / rps - 1024; if (want > smem && want <= h->smem_optin) smem = want; }
+            }
+            (spec ? sim_spec(nu, lean ? 1 : (vlean ? 2 : 0))
+                  : (lean ? sim_lean(nu, bk.P) : (vlean ? sim_vlean(nu, bk.P) : sim_kernel(nu, bk.P))))<<<grid, 32, smem, h->pool[b % NSTREAM]>>>(L, T, h->dOrder.p + bk.off, bk.count, runs, cost_mode,
                                                                            square, item0, C, O);
+            if (spec) {
+                // second pass, same stream: the (rare, ~1 %) candidates whose QP needs more active constraints than the
+                // speculative kernel keeps in shared memory run again on the kernel with the spill area; every other
+                // CTA of this launch exits on its first instruction
+                CK(cudaGetLastError());
+                const size_t smem2 = sim_smem_doubles(L, nu, bk.P) * sizeof(double);
+                (lean ? sim_lean(nu, bk.P) : (vlean ? sim_vlean(nu, bk.P) : sim_kernel(nu, bk.P)))<<<grid, 32, smem2, h->pool[b % NSTREAM]>>>(
+                    L, T, h->dOrder.p + bk.off, bk.count, runs, cost_mode | 256, square, item0, C, O);
+                launches++;
+            }
         }
         CK(cudaGetLastError());
         item0 += grid;
@@ -502,6 +547,10 @@ extern "C" int mpcgpu_run(mpcgpu_handle *h, int cost_mode, int want_traj, void *
     for (int i = 0; i < nfork; ++i) {
         CK(cudaEventRecord(h->ev_join[i], h->pool[i]));
         CK(cudaStreamWaitEvent(s, h->ev_join[i], 0));
+    }
+    if (!L.has_ov_bounds && n > 0) {
+        k_merge_status<<<(n + 127) / 128, 128, 0, s>>>(n, h->dStatus.p, h->dStatus2.p);
+        launches++;
     }
     if (cost_mode == MPCGPU_COST_VNS && n > 0) {
         k_finish_vns<<<(n + 127) / 128, 128, 0, s>>>(n, runs, h->dN.p, h->dPart.p, h->dStatus.p, h->dCost.p);

@@ -10,12 +10,17 @@ double *g_soft_dump = nullptr;
 int g_soft_dump_k = -1, g_soft_k = -2;
 extern "C" void emu_soft_dump(double *p, int k) { g_soft_dump = p; g_soft_dump_k = k; }
 int g_sim_verbose = 0;
+long long g_spec_overflow = 0;
+extern "C" long long emu_spec_overflows() { long long r = g_spec_overflow; g_spec_overflow = 0; return r; }
+long long g_spec_blocks = 0, g_spec_samples = 0, g_spec_fail = 0, g_spec_replay = 0;
+extern "C" void emu_spec_stats(long long *o) { o[0] = g_spec_blocks; o[1] = g_spec_samples; o[2] = g_spec_fail; o[3] = g_spec_replay; g_spec_blocks = g_spec_samples = g_spec_fail = g_spec_replay = 0; }
 extern "C" void emu_set_verbose(int v) { g_sim_verbose = v; }
 long long g_sim_reappends = 0, g_sim_rotations = 0;
 extern "C" long long emu_rotations() { long long r = g_sim_rotations; g_sim_rotations = 0; return r; }
 extern "C" void emu_set_knob(int k) { g_sim_knob = k; }
 extern "C" long long emu_reappends() { long long r = g_sim_reappends; g_sim_reappends = 0; return r; }
 
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -24,6 +29,7 @@ extern "C" long long emu_reappends() { long long r = g_sim_reappends; g_sim_reap
 
 #include "../../model-predictive-control-tuning_b200/csrc/mpc_core.cuh"
 #include "../../model-predictive-control-tuning_b200/csrc/mpc_sim.cuh"
+#include "../../model-predictive-control-tuning_b200/csrc/mpc_sim_spec.cuh"
 #include "../../model-predictive-control-tuning_b200/csrc/mpc_soft.cuh"
 #include "../../model-predictive-control-tuning_b200/csrc/mpc_tables.h"
 
@@ -31,6 +37,17 @@ template <int NU>
 static int sim_p(int P, const MpcLayout &L, const MpcTables &T, int m, const double *Mg, const double *Wg, int mode, int sel,
                  double *smem, double *gscr, const MpcRunOut &out) {
     double *slot = gscr + sim_scratch_doubles(NU * P);
+    if (sim_spec_ok(L) && P == 16 && !(g_sim_knob & 256)) {   // the kernel the product runs for plants whose deviation state fits one warp
+        int st;
+        switch (P) {
+            case 4: st = sim_run_spec<NU, 4>(L, T, m, Mg, Wg, mode, sel, smem, gscr, out, slot); break;
+            case 8: st = sim_run_spec<NU, 8>(L, T, m, Mg, Wg, mode, sel, smem, gscr, out, slot); break;
+            default: st = sim_run_spec<NU, 16>(L, T, m, Mg, Wg, mode, sel, smem, gscr, out, slot); break;
+        }
+        if (st != SIM_ST_OVERFLOW) return st;
+        if (threadIdx.x == 0) g_spec_overflow += 1;
+        __syncwarp();   // second pass: the kernel with the spill area, as mpcgpu_run does
+    }
     switch (P) {
         case 4: return sim_run<NU, 4>(L, T, m, Mg, Wg, mode, sel, smem, gscr, out, slot);
         case 8: return sim_run<NU, 8>(L, T, m, Mg, Wg, mode, sel, smem, gscr, out, slot);
@@ -79,8 +96,8 @@ static int run_block(int nu, int P, const MpcLayout &L, const MpcTables &T, int 
 // one warp = 32 host threads
 static int run_warp(int nu, int P, const MpcLayout &L, const MpcTables &T, int m, const double *Mg, const double *Wg, int mode,
                     int sel, const MpcRunOut &out) {
-    std::vector<double> smem(sim_smem_doubles(L, nu, P) + 8, std::nan(""));   // NaN-poison: catches reads of unwritten shared memory
-    std::vector<double> gscr(sim_scratch_doubles(nu * P) + sim_slot_doubles(nu * P) + 8, std::nan(""));
+    std::vector<double> smem(std::max(sim_spec_smem_doubles(L, nu, P), sim_smem_doubles(L, nu, P)) + 8, std::nan(""));   // NaN-poison: catches reads of unwritten shared memory
+    std::vector<double> gscr(sim_scratch_doubles(nu * P) + std::max(sim_slot_doubles(nu * P), sim_spec_slot_doubles(nu * P)) + 8, std::nan(""));
     int status[32];
     simt_run_warp([&]() {
         status[threadIdx.x] = sim_dispatch(nu, P, L, T, m, Mg, Wg, mode, sel, smem.data(), gscr.data(), out);
@@ -101,7 +118,7 @@ extern "C" int emu_eval_batch(const mpcgpu_problem *pb, int n, const int *N, con
     if (!e.empty()) { std::strncpy(err, e.c_str(), errlen - 1); return 1; }
     const MpcLayout &L = ht.L;
     MpcTables T{ht.TG.data(), ht.TK.data(), ht.S1.data(), ht.r.data(), ht.v.data(), ht.yref.data(),
-                ht.step.data(), ht.pa.data(), L.pmax + L.mmax + 2};
+                ht.step.data(), ht.pa.data(), L.pmax + L.mmax + 2, ht.sig.data()};
     const int ny = L.ny, nu = L.nu, nit = L.nit;
     const bool square = ny == nu;
     for (int c = 0; c < n; ++c) {
@@ -112,7 +129,7 @@ extern "C" int emu_eval_batch(const mpcgpu_problem *pb, int n, const int *N, con
             if (cost && mode == 2) cost[c] = NAN;
             continue;
         }
-        const int P = sim_pad(m), R = nu * P;
+        const int P = (sim_spec_ok(L) && !(g_sim_knob & 512)) ? 16 : sim_pad(m), R = nu * P;   // the product runs one P = 16 image (knob 512: size buckets, plain kernel)
         std::vector<double> bsm(mpc_builder_smem_doubles(nz, L.nst));
         std::vector<double> Mg((size_t)L.nst * R), Wg((size_t)2 * R * R);
         int flag = 0;
@@ -153,5 +170,5 @@ extern "C" int emu_eval_batch(const mpcgpu_problem *pb, int n, const int *N, con
 extern "C" long long emu_sim_smem_bytes(const mpcgpu_problem *pb, int P) {
     MpcHostTables ht;
     if (!mpc_build_tables(*pb, ht).empty()) return -1;
-    return (long long)(sim_smem_doubles(ht.L, ht.L.nu, P) * sizeof(double));
+    return (long long)((sim_spec_ok(ht.L) ? sim_spec_smem_doubles(ht.L, ht.L.nu, P) : sim_smem_doubles(ht.L, ht.L.nu, P)) * sizeof(double));
 }

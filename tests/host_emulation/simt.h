@@ -90,6 +90,15 @@ static inline unsigned __reduce_min_sync(unsigned, unsigned v) {
     simt_warp->bar.arrive_and_wait();
     return r;
 }
+static inline unsigned __reduce_or_sync(unsigned, unsigned v) {
+    simt_warp->vote[threadIdx.x & 31] = v;
+    simt_warp->bar.arrive_and_wait();
+    unsigned r = 0u;
+    for (int i = 0; i < 32; ++i) r |= simt_warp->vote[i];
+    simt_warp->bar.arrive_and_wait();
+    return r;
+}
+static inline int __ffs(int v) { return __builtin_ffs(v); }
 static inline unsigned __reduce_xor_sync(unsigned, unsigned v) {
     simt_warp->vote[threadIdx.x & 31] = v;
     simt_warp->bar.arrive_and_wait();
