@@ -517,6 +517,7 @@ extern "C" int mpcgpu_run(mpcgpu_handle *h, int cost_mode, int want_traj, void *
             static const bool spec_off = getenv("MPCGPU_SPEC") && atoi(getenv("MPCGPU_SPEC")) == 0;
             const bool spec = sim_spec_ok(L) && bk.P == 16 && !spec_off;
             const bool lean = cost_mode == MPCGPU_COST_GAM && !want_traj && !h->want_diag;   // the tuning loop's call
+            const bool vlean = cost_mode == MPCGPU_COST_VNS && !want_traj && !h->want_diag;   // ... and its VNS phase
             size_t smem = (spec ? sim_spec_smem_doubles(L, nu, bk.P, lean) : sim_smem_doubles(L, nu, bk.P)) * sizeof(double);
             {   // Resident runs per SM.  The kernel is bound by instruction fetch: co-resident runs slow
                 // each other down, so a SMALL population, whose step lasts as long as its heaviest run, finishes sooner with
