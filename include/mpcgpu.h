@@ -41,7 +41,8 @@ enum {
     MPCGPU_CAND_INFEASIBLE = 1,   /* QP infeasible (cannot happen with MV box + rate limits only) */
     MPCGPU_CAND_ITER_CAP = 2,     /* active-set iteration cap hit                                 */
     MPCGPU_CAND_NOT_PD = 3,       /* Hessian not positive definite (lambda == 0 and rank-deficient G) */
-    MPCGPU_CAND_INVALID = 4,      /* horizons illegal: PreCon.m:23 / VNS2.m:135 (only if check_valid) */
+    MPCGPU_CAND_INVALID = 4,      /* horizons illegal: p < 2, m < 1, m >= p, beyond pmax / mmax; with MPCGPU_OPT_VNS_LEGALITY also
+                                     VNS2.m:135 (N <= dmin_i for some output, Nu <= 1) -- PreCon.m:23 is m >= p            */
     MPCGPU_CAND_BOUND_CROSSED = 5 /* NMPC only: a state/OV bound (soft in the Toolbox, not enforced here) was crossed; cost is still returned */
 };
 
@@ -93,7 +94,8 @@ int mpcgpu_create(const mpcgpu_problem *problem, int device, mpcgpu_handle **out
 void mpcgpu_destroy(mpcgpu_handle *h);
 
 /* Replace the signals (closedloop_toolbox takes r, v, nit per call: closedloop_toolbox.m:1).
- * r: nit x ny, v: nit x nd (may be NULL when nd == 0), yref: ny x nit (may be NULL -> zeros). */
+ * r: nit x ny, v: nit x nd (may be NULL when nd == 0), yref: ny x nit; yref == NULL keeps the current reference trajectory
+ * when nit is unchanged and zero-fills it otherwise. */
 int mpcgpu_set_signals(mpcgpu_handle *h, int nit, const double *r, const double *v, const double *yref);
 
 /* One call = one population.  HOST pointers; copies in, runs, copies out, synchronises.
@@ -117,11 +119,48 @@ int mpcgpu_run(mpcgpu_handle *h, int cost_mode, int want_traj, void *cuda_stream
 int mpcgpu_download(mpcgpu_handle *h, int cost_mode, double *cost, double *y, double *u, double *ys,
                     double *uopt, int32_t *status);
 /* Device pointer of the cost buffer of the last run (n x ny or n doubles), for on-device consumers
- * such as an NCCL all-gather of fitness. */
+ * such as an NCCL all-gather of fitness.  The consumer must order itself after the run on the run's stream; the next
+ * mpcgpu_upload / mpcgpu_run on this handle waits for the previous run before it touches the buffers. */
 int mpcgpu_cost_device_ptr(mpcgpu_handle *h, int cost_mode, void **ptr, int *count);
+
+/* Options.  MPCGPU_OPT_VNS_LEGALITY = 1: candidates the VNS search would reject before evaluating them
+ * (VNS2.m:135  any(N<=dmin) | any(Nu<=1), dmin = problem.dmin, MPCTuning.m:257-262) get MPCGPU_CAND_INVALID and a NaN
+ * cost instead of being simulated.  Off by default: closedloop_toolbox.m and GAM_fun.m themselves accept them. */
+enum { MPCGPU_OPT_VNS_LEGALITY = 1 };
+int mpcgpu_set_option(mpcgpu_handle *h, int option, int value);
+
+/* [y,u,t,ys,uopt] = closedloop_toolbox(mpc_toolbox,r,v,N,Nu,delta,lambda,nit) as ONE call
+ * (/root/reference/MPC-Tuning/MPC_Tuning/closedloop_toolbox.m:1): r nit x ny, v nit x nd (NULL when nd == 0), N / Nu the
+ * max of the caller's vectors (:38-40), outputs signals x time (ny|nu x nit, :103-107; any may be NULL), t = (0..nit-1)*Ts
+ * is the caller's.  The call's signals are used for this evaluation only: the handle's own set-point, disturbance,
+ * reference trajectory and nit (Par.Xsp, Par.mdv, Par.Yref) are unchanged afterwards, so GAM / VNS costs evaluated
+ * before and after are identical -- the reference's closedloop_toolbox never touches Par. */
+int mpcgpu_closedloop(mpcgpu_handle *h, int nit, const double *r, const double *v, int32_t N, int32_t Nu,
+                      const double *delta, const double *lambda, double *y, double *u, double *ys, double *uopt,
+                      int32_t *status);
 
 int mpcgpu_get_counters(mpcgpu_handle *h, mpcgpu_counters *out);
 const char *mpcgpu_last_error(mpcgpu_handle *h); /* h may be NULL: last create() error */
+
+/* Multi-GPU evaluator: one evaluator per listed device inside ONE process (what a MEX gateway needs
+ * to use the 8 B200s of a box).  mpcgpu_multi_eval_batch deals the candidates by estimated work (sorted round-robin),
+ * launches every device asynchronously and gathers the fitness (and status) into the caller's host arrays in population
+ * order; costs only (GAM: n x ny, VNS: n).  Results are bit-identical to the single-device call: a candidate's cost does
+ * not depend on its position in a population or on the device.  devices == NULL: 0 .. ndev-1.
+ * (One process per GPU -- torchrun, bench.py -- shards with the same key, mpcgpu_work_estimate, and all-gathers with NCCL.) */
+typedef struct mpcgpu_multi mpcgpu_multi;
+int mpcgpu_create_multi(const mpcgpu_problem *problem, const int *devices, int ndev, mpcgpu_multi **out);
+void mpcgpu_destroy_multi(mpcgpu_multi *m);
+int mpcgpu_multi_device_count(mpcgpu_multi *m);
+int mpcgpu_multi_set_option(mpcgpu_multi *m, int option, int value);
+int mpcgpu_multi_set_signals(mpcgpu_multi *m, int nit, const double *r, const double *v, const double *yref);
+int mpcgpu_multi_eval_batch(mpcgpu_multi *m, int n, const int32_t *N, const int32_t *Nu, const double *delta,
+                            const double *lambda, int cost_mode, double *cost, int32_t *status);
+int mpcgpu_multi_get_counters(mpcgpu_multi *m, int device_index, mpcgpu_counters *out);
+const char *mpcgpu_multi_last_error(mpcgpu_multi *m); /* m may be NULL: last create error */
+/* work[c]: relative a-priori cost of candidate c (moves, aggressiveness of the weights, horizons barely past the dead time) */
+int mpcgpu_work_estimate(const mpcgpu_problem *problem, int n, const int32_t *N, const int32_t *Nu, const double *delta,
+                         const double *lambda, double *work);
 int mpcgpu_device_count(void);
 
 /* fp64 FMA throughput microbenchmark (TFLOP/s, 2 flops per FMA) used as the roofline denominator of
@@ -162,6 +201,7 @@ void mpcgpu_dtc_destroy(mpcgpu_dtc_handle *h);
 int mpcgpu_dtc_eval_batch(mpcgpu_dtc_handle *h, int n, const int32_t *p, const int32_t *m, const double *delta,
                           const double *lambda, const double *fr_num, const double *fr_den, const int32_t *fr_len,
                           double *ise, double *y, double *u, int32_t *status);
+int mpcgpu_dtc_get_counters(mpcgpu_dtc_handle *h, mpcgpu_counters *out); /* candidates, kernel_launches, last_sim_ms (device time of k_dtc) */
 const char *mpcgpu_dtc_last_error(mpcgpu_dtc_handle *h);
 /* Host-only (no CUDA call): the candidate-independent polynomial tables the sweep is built from -- step responses
  * (MatG.m:51), Diophantine F rows (diophantine.m:55-65), past-control rows (deltaUFree.m:36-57).  info: 64 ints

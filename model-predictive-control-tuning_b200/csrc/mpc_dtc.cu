@@ -335,6 +335,7 @@ struct mpcgpu_dtc_handle {
     cudaStream_t stream = nullptr;
     double *dStep = nullptr, *dF = nullptr, *dUg = nullptr, *dR = nullptr, *dQ = nullptr;
     size_t smem_optin = 0;
+    mpcgpu_counters cnt = {};
 };
 static std::string g_dtc_create_error;
 
@@ -441,14 +442,28 @@ extern "C" int mpcgpu_dtc_eval_batch(mpcgpu_dtc_handle *h, int n, const int32_t 
         DtcCand Cd{dp, dm, ddl, dlm, dfn, dfd, dfl, dise, y ? dy : nullptr, u ? du : nullptr, dst};
         DtcTables T{h->dStep, h->dF, h->dUg, h->dR, h->dQ, h->ht.step_len};
         const size_t smem = dtc_plan(L).doubles * sizeof(double) * DTC_WARPS;
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        cudaEventCreate(&e0); cudaEventCreate(&e1);
+        cudaEventRecord(e0, s);
         k_dtc<<<(n + DTC_WARPS - 1) / DTC_WARPS, 32 * DTC_WARPS, smem, s>>>(L, T, n, Cd);
         ck(cudaGetLastError());
+        cudaEventRecord(e1, s);
         ck(cudaMemcpyAsync(ise, dise, sizeof(double) * (size_t)n * ny, cudaMemcpyDeviceToHost, s));
         if (y) ck(cudaMemcpyAsync(y, dy, sizeof(double) * (size_t)n * ny * nit, cudaMemcpyDeviceToHost, s));
         if (u) ck(cudaMemcpyAsync(u, du, sizeof(double) * (size_t)n * nu * nit, cudaMemcpyDeviceToHost, s));
         if (status) ck(cudaMemcpyAsync(status, dst, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, s));
         ck(cudaStreamSynchronize(s));
+        float ms = 0.f;
+        if (rc == MPCGPU_OK && cudaEventElapsedTime(&ms, e0, e1) == cudaSuccess) { h->cnt.last_sim_ms = ms; h->cnt.last_total_ms = ms; }
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        h->cnt.candidates += n; h->cnt.closed_loops += n; h->cnt.kernel_launches += 1;
     }
     cudaFree(dI); cudaFree(dD);
     return rc;
+}
+
+extern "C" int mpcgpu_dtc_get_counters(mpcgpu_dtc_handle *h, mpcgpu_counters *out) {
+    if (!h || !out) return MPCGPU_ERR_ARG;
+    *out = h->cnt;
+    return MPCGPU_OK;
 }

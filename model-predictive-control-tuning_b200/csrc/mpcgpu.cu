@@ -190,6 +190,7 @@ struct mpcgpu_handle {
     mpcgpu_counters cnt = {};
     size_t smem_optin = 0;
     int sm_count = 148;
+    int opt_vns_legality = 0;   // MPCGPU_OPT_VNS_LEGALITY
 };
 
 static MpcTables dev_tables(mpcgpu_handle *h) {
@@ -267,12 +268,11 @@ extern "C" int mpcgpu_create(const mpcgpu_problem *problem, int device, mpcgpu_h
     if ((ce = h->dS1.ensure(t.S1.size())) != cudaSuccess) return fail("alloc S1", ce);
     if ((ce = h->dST.ensure(t.step.size())) != cudaSuccess) return fail("alloc ST", ce);
     if ((ce = h->dPA.ensure(t.pa.size())) != cudaSuccess) return fail("alloc PA", ce);
-    cudaMemcpy(h->dST.p, t.step.data(), t.step.size() * sizeof(double), cudaMemcpyHostToDevice);
-    cudaMemcpy(h->dPA.p, t.pa.data(), t.pa.size() * sizeof(double), cudaMemcpyHostToDevice);
-    cudaMemcpy(h->dTG.p, t.TG.data(), t.TG.size() * sizeof(double), cudaMemcpyHostToDevice);
-    cudaMemcpy(h->dTK.p, t.TK.data(), t.TK.size() * sizeof(double), cudaMemcpyHostToDevice);
-    ce = cudaMemcpy(h->dS1.p, t.S1.data(), t.S1.size() * sizeof(double), cudaMemcpyHostToDevice);
-    if (ce != cudaSuccess) return fail("copy tables", ce);
+    if ((ce = cudaMemcpy(h->dST.p, t.step.data(), t.step.size() * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess) return fail("copy step table", ce);
+    if ((ce = cudaMemcpy(h->dPA.p, t.pa.data(), t.pa.size() * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess) return fail("copy pole table", ce);
+    if ((ce = cudaMemcpy(h->dTG.p, t.TG.data(), t.TG.size() * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess) return fail("copy TG", ce);
+    if ((ce = cudaMemcpy(h->dTK.p, t.TK.data(), t.TK.size() * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess) return fail("copy TK", ce);
+    if ((ce = cudaMemcpy(h->dS1.p, t.S1.data(), t.S1.size() * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess) return fail("copy S1", ce);
     if (upload_signals(h) != MPCGPU_OK) { g_create_error = h->err; mpcgpu_destroy(h); return MPCGPU_ERR_CUDA; }
     if ((ce = h->dCounters.ensure(4)) != cudaSuccess) return fail("alloc counters", ce);
     // allow large dynamic shared memory on both kernels
@@ -280,10 +280,9 @@ extern "C" int mpcgpu_create(const mpcgpu_problem *problem, int device, mpcgpu_h
     if ((ce = cudaFuncSetAttribute(k_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin - 1024)) != cudaSuccess)
         return fail("cudaFuncSetAttribute(k_build)", ce);
     for (int P = 4; P <= 16; P *= 2) {
-        cudaFuncSetAttribute(sim_kernel(t.L.nu, P), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin);
-        cudaFuncSetAttribute(sim_lean(t.L.nu, P), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin);
-        cudaFuncSetAttribute(sim_vlean(t.L.nu, P), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin);
-        cudaFuncSetAttribute(soft_kernel(t.L.nu, P), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin);
+        for (sim_kernel_t kf : {sim_kernel(t.L.nu, P), sim_lean(t.L.nu, P), sim_vlean(t.L.nu, P), soft_kernel(t.L.nu, P)})
+            if ((ce = cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin)) != cudaSuccess)
+                return fail("cudaFuncSetAttribute(closed-loop kernel)", ce);
     }
     for (int v = 0; v < 3; ++v)
         if ((ce = cudaFuncSetAttribute(sim_spec(t.L.nu, v), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin)) != cudaSuccess)
@@ -335,6 +334,8 @@ extern "C" void mpcgpu_destroy(mpcgpu_handle *h) {
 extern "C" int mpcgpu_set_signals(mpcgpu_handle *h, int nit, const double *r, const double *v, const double *yref) {
     if (!h) return MPCGPU_ERR_ARG;
     CK(cudaSetDevice(h->device));
+    std::vector<double> keep;
+    if (!yref && nit == h->ht.L.nit && (int)h->ht.yref.size() == nit * h->ht.L.ny) { keep = h->ht.yref; yref = keep.data(); }   // NULL: keep Par.Yref
     std::string e = mpc_set_signals(h->ht, nit, r, v, yref);
     if (!e.empty()) { h->err = e; return MPCGPU_ERR_ARG; }
     return upload_signals(h);
@@ -345,6 +346,8 @@ extern "C" int mpcgpu_upload(mpcgpu_handle *h, int n, const int32_t *N, const in
     if (!h) return MPCGPU_ERR_ARG;
     if (n < 0 || (n > 0 && (!N || !Nu || !delta || !lambda))) { h->err = "bad population arguments"; return MPCGPU_ERR_ARG; }
     CK(cudaSetDevice(h->device));
+    // a previous run (possibly on a caller stream) may still be reading the population buffers this call overwrites
+    if (h->ran) CK(cudaEventSynchronize(h->ev_t2));
     const MpcLayout &L = h->ht.L;
     const int ny = L.ny, nu = L.nu;
     h->n = n; h->uploaded = false; h->ran = false;
@@ -358,7 +361,12 @@ extern "C" int mpcgpu_upload(mpcgpu_handle *h, int n, const int32_t *N, const in
     h->n_valid = 0;
     for (int c = 0; c < n; ++c) {
         const int p = N[c], m = Nu[c];
-        if (p < 2 || p > L.pmax || m < 1 || m > L.mmax || m >= p) { h->hInvalid[c] = 1; continue; }
+        bool illegal = p < 2 || p > L.pmax || m < 1 || m > L.mmax || m >= p;
+        if (!illegal && h->opt_vns_legality) {   // VNS2.m:135  any(N<=dmin) | any(Nu<=1)   (PreCon.m:23: min(N) > max(Nu))
+            if (m <= 1) illegal = true;
+            for (int i = 0; i < ny && !illegal; ++i) illegal = p <= h->ht.dmin[i];
+        }
+        if (illegal) { h->hInvalid[c] = 1; continue; }
         // One kernel image for the whole population: three concurrently running instantiations
         // (P = 4, 8, 16, ~240 KB of SASS each) thrashed the instruction cache -- measured 16.3 ms against 10.8 ms for
         // 4096 Shell3x3 candidates with everything on the P = 16 image (Shell7x5 / k_soft: 455 -> 418 ms).
@@ -473,6 +481,7 @@ extern "C" int mpcgpu_run(mpcgpu_handle *h, int cost_mode, int want_traj, void *
     }
     h->last_runs = runs;
     const MpcTables T = dev_tables(h);
+    if (h->ran) CK(cudaStreamWaitEvent(s, h->ev_t2, 0));   // two runs in flight would race on status / counters / cost
     CK(cudaEventRecord(h->ev_t0, s));
     CK(cudaMemsetAsync(h->dStatus.p, 0, sizeof(int) * nn, s));
     CK(cudaMemsetAsync(h->dStatus2.p, 0, sizeof(int) * nn, s));
@@ -630,6 +639,154 @@ extern "C" int mpcgpu_get_counters(mpcgpu_handle *h, mpcgpu_counters *out) {
     if (!h || !out) return MPCGPU_ERR_ARG;
     *out = h->cnt;
     return MPCGPU_OK;
+}
+
+extern "C" int mpcgpu_set_option(mpcgpu_handle *h, int option, int value) {
+    if (!h) return MPCGPU_ERR_ARG;
+    switch (option) {
+        case MPCGPU_OPT_VNS_LEGALITY: h->opt_vns_legality = value != 0; return MPCGPU_OK;
+    }
+    h->err = "unknown option";
+    return MPCGPU_ERR_ARG;
+}
+
+// closedloop_toolbox.m:1 as ONE call: the signals of the call are installed for this evaluation only and the handle's
+// own (Par.Xsp, Par.mdv, Par.Yref, nit) are put back afterwards -- the reference never touches Par in closedloop_toolbox,
+// and VNS2 interleaves these calls with GAM_fun on the same Par.
+extern "C" int mpcgpu_closedloop(mpcgpu_handle *h, int nit, const double *r, const double *v, int32_t N, int32_t Nu,
+                                 const double *delta, const double *lambda, double *y, double *u, double *ys, double *uopt,
+                                 int32_t *status) {
+    if (!h || !r || !delta || !lambda) return MPCGPU_ERR_ARG;
+    const std::vector<double> r0 = h->ht.r, v0 = h->ht.v, y0 = h->ht.yref;
+    const int nit0 = h->ht.L.nit;
+    int rc = mpcgpu_set_signals(h, nit, r, v, nullptr);
+    if (rc == MPCGPU_OK) {
+        if (nit != nit0) { /* yref was zero-filled: irrelevant for RAW */ }
+        rc = mpcgpu_eval_batch(h, 1, &N, &Nu, delta, lambda, MPCGPU_COST_RAW, nullptr, y, u, ys, uopt, status);
+    }
+    const std::string err = h->err;
+    const int rc2 = mpcgpu_set_signals(h, nit0, r0.data(), h->ht.L.nd > 0 ? v0.data() : nullptr, y0.data());
+    if (rc != MPCGPU_OK) { h->err = err; return rc; }
+    return rc2;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Multi-GPU evaluator: one handle per device of ONE process, candidates dealt by estimated work (sorted round-robin,
+// SURVEY.md 8e), every device runs asynchronously, fitness gathered into the caller's host arrays in population order.
+// ------------------------------------------------------------------------------------------------
+struct mpcgpu_multi {
+    std::vector<mpcgpu_handle *> hs;
+    std::string err;
+    std::vector<std::vector<int>> shard;
+    std::vector<std::vector<int32_t>> sN, sNu, sStatus;
+    std::vector<std::vector<double>> sDelta, sLambda, sCost;
+};
+
+extern "C" int mpcgpu_create_multi(const mpcgpu_problem *problem, const int *devices, int ndev, mpcgpu_multi **out) {
+    if (!problem || !out || ndev < 1) { g_create_error = "NULL argument / ndev < 1"; return MPCGPU_ERR_ARG; }
+    *out = nullptr;
+    mpcgpu_multi *m = new mpcgpu_multi();
+    for (int d = 0; d < ndev; ++d) {
+        mpcgpu_handle *h = nullptr;
+        const int rc = mpcgpu_create(problem, devices ? devices[d] : d, &h);
+        if (rc != MPCGPU_OK) { for (auto *x : m->hs) mpcgpu_destroy(x); delete m; return rc; }
+        m->hs.push_back(h);
+    }
+    m->shard.resize(ndev); m->sN.resize(ndev); m->sNu.resize(ndev); m->sStatus.resize(ndev);
+    m->sDelta.resize(ndev); m->sLambda.resize(ndev); m->sCost.resize(ndev);
+    *out = m;
+    return MPCGPU_OK;
+}
+extern "C" void mpcgpu_destroy_multi(mpcgpu_multi *m) {
+    if (!m) return;
+    for (auto *h : m->hs) mpcgpu_destroy(h);
+    delete m;
+}
+extern "C" int mpcgpu_multi_device_count(mpcgpu_multi *m) { return m ? (int)m->hs.size() : 0; }
+extern "C" const char *mpcgpu_multi_last_error(mpcgpu_multi *m) { return m ? m->err.c_str() : g_create_error.c_str(); }
+extern "C" int mpcgpu_multi_set_option(mpcgpu_multi *m, int option, int value) {
+    if (!m) return MPCGPU_ERR_ARG;
+    for (auto *h : m->hs) { const int rc = mpcgpu_set_option(h, option, value); if (rc) { m->err = h->err; return rc; } }
+    return MPCGPU_OK;
+}
+extern "C" int mpcgpu_multi_set_signals(mpcgpu_multi *m, int nit, const double *r, const double *v, const double *yref) {
+    if (!m) return MPCGPU_ERR_ARG;
+    for (auto *h : m->hs) { const int rc = mpcgpu_set_signals(h, nit, r, v, yref); if (rc) { m->err = h->err; return rc; } }
+    return MPCGPU_OK;
+}
+// The a-priori work estimate the shards are balanced on (also exported: the multi-process path -- one rank per GPU,
+// bench.py / mpcgpu.distributed -- deals with the same key).
+extern "C" int mpcgpu_work_estimate(const mpcgpu_problem *pb, int n, const int32_t *N, const int32_t *Nu, const double *delta,
+                                    const double *lambda, double *work) {
+    if (!pb || !N || !Nu || !delta || !lambda || !work) return MPCGPU_ERR_ARG;
+    int dead_max = 0;
+    for (int ch = 0; ch < pb->ny * (pb->nu + pb->nd); ++ch) dead_max = std::max(dead_max, (int)pb->d[ch]);
+    for (int c = 0; c < n; ++c) {
+        double dmax = 0.0, lmin = 1e300;
+        for (int i = 0; i < pb->ny; ++i) dmax = std::max(dmax, std::fabs(delta[(size_t)c * pb->ny + i]));
+        for (int j = 0; j < pb->nu; ++j) lmin = std::min(lmin, std::fabs(lambda[(size_t)c * pb->nu + j]));
+        work[c] = std::log10(dmax / (lmin + 1e-300) + 1e-300) + 0.15 * Nu[c] + (N[c] <= dead_max + 2 ? 2.0 : 0.0);
+    }
+    return MPCGPU_OK;
+}
+extern "C" int mpcgpu_multi_eval_batch(mpcgpu_multi *m, int n, const int32_t *N, const int32_t *Nu, const double *delta,
+                                       const double *lambda, int cost_mode, double *cost, int32_t *status) {
+    if (!m) return MPCGPU_ERR_ARG;
+    if (cost_mode != MPCGPU_COST_GAM && cost_mode != MPCGPU_COST_VNS) { m->err = "multi-GPU evaluation returns costs only (GAM or VNS)"; return MPCGPU_ERR_ARG; }
+    if (n < 0 || (n > 0 && (!N || !Nu || !delta || !lambda || !cost))) { m->err = "bad population arguments"; return MPCGPU_ERR_ARG; }
+    const int G = (int)m->hs.size();
+    const MpcLayout &L = m->hs[0]->ht.L;
+    const int ny = L.ny, nu = L.nu, width = cost_mode == MPCGPU_COST_GAM ? ny : 1;
+    // deal by work: sorted, round-robin
+    std::vector<double> work(n);
+    {
+        int dead_max = 0;
+        for (int ch = 0; ch < ny * L.nw; ++ch) dead_max = std::max(dead_max, (int)L.d[ch]);
+        for (int c = 0; c < n; ++c) {
+            double dmax = 0.0, lmin = 1e300;
+            for (int i = 0; i < ny; ++i) dmax = std::max(dmax, std::fabs(delta[(size_t)c * ny + i]));
+            for (int j = 0; j < nu; ++j) lmin = std::min(lmin, std::fabs(lambda[(size_t)c * nu + j]));
+            work[c] = std::log10(dmax / (lmin + 1e-300) + 1e-300) + 0.15 * Nu[c] + (N[c] <= dead_max + 2 ? 2.0 : 0.0);
+        }
+    }
+    std::vector<int> order(n);
+    for (int c = 0; c < n; ++c) order[c] = c;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return work[a] > work[b]; });
+    for (int g = 0; g < G; ++g) { m->shard[g].clear(); }
+    for (int k = 0; k < n; ++k) m->shard[k % G].push_back(order[k]);
+    // phase 1: upload + launch on every device (mpcgpu_run is asynchronous)
+    for (int g = 0; g < G; ++g) {
+        const auto &sh = m->shard[g];
+        const int ns = (int)sh.size();
+        m->sN[g].resize(ns); m->sNu[g].resize(ns); m->sDelta[g].resize((size_t)ns * ny); m->sLambda[g].resize((size_t)ns * nu);
+        for (int k = 0; k < ns; ++k) {
+            const int c = sh[k];
+            m->sN[g][k] = N[c]; m->sNu[g][k] = Nu[c];
+            std::memcpy(&m->sDelta[g][(size_t)k * ny], delta + (size_t)c * ny, sizeof(double) * ny);
+            std::memcpy(&m->sLambda[g][(size_t)k * nu], lambda + (size_t)c * nu, sizeof(double) * nu);
+        }
+        int rc = mpcgpu_upload(m->hs[g], ns, m->sN[g].data(), m->sNu[g].data(), m->sDelta[g].data(), m->sLambda[g].data());
+        if (rc == MPCGPU_OK) rc = mpcgpu_run(m->hs[g], cost_mode, 0, nullptr);
+        if (rc != MPCGPU_OK) { m->err = m->hs[g]->err; return rc; }
+    }
+    // phase 2: gather (the per-generation "all-gather" of a single-process caller: host arrays in population order)
+    for (int g = 0; g < G; ++g) {
+        const auto &sh = m->shard[g];
+        const int ns = (int)sh.size();
+        m->sCost[g].resize((size_t)ns * width + 1); m->sStatus[g].resize(ns + 1);
+        const int rc = mpcgpu_download(m->hs[g], cost_mode, m->sCost[g].data(), nullptr, nullptr, nullptr, nullptr, m->sStatus[g].data());
+        if (rc != MPCGPU_OK) { m->err = m->hs[g]->err; return rc; }
+        for (int k = 0; k < ns; ++k) {
+            const int c = sh[k];
+            std::memcpy(cost + (size_t)c * width, &m->sCost[g][(size_t)k * width], sizeof(double) * width);
+            if (status) status[c] = m->sStatus[g][k];
+        }
+    }
+    return MPCGPU_OK;
+}
+extern "C" int mpcgpu_multi_get_counters(mpcgpu_multi *m, int device_index, mpcgpu_counters *out) {
+    if (!m || !out || device_index < 0 || device_index >= (int)m->hs.size()) return MPCGPU_ERR_ARG;
+    return mpcgpu_get_counters(m->hs[device_index], out);
 }
 
 extern "C" int mpcgpu_measure_fp64_peak(int device, double *tflops) {

@@ -10,6 +10,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MPCGPU_LIB") or os.path.join(os.path.dirname(_PKG), "csrc", "libmpcgpu.so")   # MPCGPU_LIB: A/B builds
 
 COST_RAW, COST_GAM, COST_VNS = 0, 1, 2
+OPT_VNS_LEGALITY = 1
 _MODES = {"raw": COST_RAW, "gam": COST_GAM, "vns": COST_VNS}
 
 
@@ -85,6 +86,19 @@ def load_library():
     lib.mpcgpu_cost_device_ptr.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int)]
     lib.mpcgpu_get_counters.argtypes = [C.c_void_p, C.POINTER(Counters)]
     lib.mpcgpu_measure_fp64_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
+    lib.mpcgpu_set_option.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    lib.mpcgpu_closedloop.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32] + [C.c_void_p] * 7
+    lib.mpcgpu_create_multi.argtypes = [C.POINTER(ProblemStruct), C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
+    lib.mpcgpu_destroy_multi.argtypes = [C.c_void_p]
+    lib.mpcgpu_destroy_multi.restype = None
+    lib.mpcgpu_multi_device_count.argtypes = [C.c_void_p]
+    lib.mpcgpu_multi_set_option.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    lib.mpcgpu_multi_set_signals.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.mpcgpu_multi_eval_batch.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 2
+    lib.mpcgpu_multi_get_counters.argtypes = [C.c_void_p, C.c_int, C.POINTER(Counters)]
+    lib.mpcgpu_multi_last_error.restype = C.c_char_p
+    lib.mpcgpu_multi_last_error.argtypes = [C.c_void_p]
+    lib.mpcgpu_work_estimate.argtypes = [C.POINTER(ProblemStruct), C.c_int] + [C.c_void_p] * 5
     lib.mpcgpu_dtc_last_error.restype = C.c_char_p
     lib.mpcgpu_dtc_last_error.argtypes = [C.c_void_p]
     lib.mpcgpu_dtc_create.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
@@ -92,6 +106,7 @@ def load_library():
     lib.mpcgpu_dtc_destroy.restype = None
     lib.mpcgpu_dtc_eval_batch.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 11
     lib.mpcgpu_dtc_host_tables.argtypes = [C.c_void_p] * 5
+    lib.mpcgpu_dtc_get_counters.argtypes = [C.c_void_p, C.POINTER(Counters)]
     lib.mpcgpu_nmpc_last_error.restype = C.c_char_p
     lib.mpcgpu_nmpc_last_error.argtypes = [C.c_void_p]
     lib.mpcgpu_nmpc_create.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
@@ -106,8 +121,11 @@ def load_library():
 EXPORTED_SYMBOLS = [
     "mpcgpu_create", "mpcgpu_destroy", "mpcgpu_set_signals", "mpcgpu_eval_batch", "mpcgpu_upload", "mpcgpu_run",
     "mpcgpu_download", "mpcgpu_cost_device_ptr", "mpcgpu_get_counters", "mpcgpu_last_error", "mpcgpu_device_count",
-    "mpcgpu_measure_fp64_peak",
+    "mpcgpu_measure_fp64_peak", "mpcgpu_set_option", "mpcgpu_closedloop",
+    "mpcgpu_create_multi", "mpcgpu_destroy_multi", "mpcgpu_multi_device_count", "mpcgpu_multi_set_option",
+    "mpcgpu_multi_set_signals", "mpcgpu_multi_eval_batch", "mpcgpu_multi_get_counters", "mpcgpu_multi_last_error",
+    "mpcgpu_work_estimate",
     "mpcgpu_dtc_create", "mpcgpu_dtc_destroy", "mpcgpu_dtc_eval_batch", "mpcgpu_dtc_last_error",
-    "mpcgpu_dtc_host_tables",
+    "mpcgpu_dtc_host_tables", "mpcgpu_dtc_get_counters",
     "mpcgpu_nmpc_create", "mpcgpu_nmpc_destroy", "mpcgpu_nmpc_eval_batch", "mpcgpu_nmpc_get_counters", "mpcgpu_nmpc_last_error",
 ]

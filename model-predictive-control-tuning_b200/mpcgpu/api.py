@@ -152,6 +152,80 @@ class Evaluator:
         self._check(self.lib.mpcgpu_get_counters(self.h, C.byref(c)), "mpcgpu_get_counters")
         return c.asdict()
 
+    def set_option(self, option: int, value: int):
+        """e.g. set_option(OPT_VNS_LEGALITY, 1): VNS2.m:135 legality (N <= dmin, Nu <= 1 -> status 4) inside the library."""
+        self._check(self.lib.mpcgpu_set_option(self.h, int(option), int(value)), "mpcgpu_set_option")
+
+    def closedloop(self, r, v, N, Nu, delta, lam, nit):
+        """mpcgpu_closedloop: one closedloop_toolbox call with per-call signals; the handle's own signals are untouched."""
+        nit = int(nit)
+        r = np.ascontiguousarray(row2col(r)[:nit])
+        vv = np.ascontiguousarray(row2col(v)[:nit]) if self.nd else None
+        delta = np.ascontiguousarray(delta, dtype=np.float64).reshape(self.ny)
+        lam = np.ascontiguousarray(lam, dtype=np.float64).reshape(self.nu)
+        y, ys = np.empty((self.ny, nit)), np.empty((self.ny, nit))
+        u, uopt = np.empty((self.nu, nit)), np.empty((self.nu, nit))
+        st = np.zeros(1, dtype=np.int32)
+        self._check(self.lib.mpcgpu_closedloop(self.h, nit, _ptr(r), _ptr(vv), int(N), int(Nu), _ptr(delta), _ptr(lam),
+                                               _ptr(y), _ptr(u), _ptr(ys), _ptr(uopt), _ptr(st)), "mpcgpu_closedloop")
+        return y, u, ys, uopt, int(st[0])
+
+
+class MultiEvaluator:
+    """`mpcgpu_multi`: the same problem on several B200s of one box, driven from ONE process (what the MEX gateway uses).
+    `eval_batch` deals the population by estimated work, runs every device concurrently and returns the costs in
+    population order -- bit-identical to a single-device `Evaluator.eval_batch`."""
+
+    def __init__(self, prob: LinearProblem, devices=None, r=None, v=None, yref=None, nit=None):
+        self.lib = _capi.load_library()
+        self.prob = prob
+        ps, self._keep = _capi.make_problem_struct(prob, r=r, v=v, yref=yref, nit=nit)
+        self.ny, self.nu, self.nd, self.nit = prob.ny, prob.nu, prob.nd, ps.nit
+        if devices is None:
+            devices = list(range(self.lib.mpcgpu_device_count()))
+        dv = np.ascontiguousarray(devices, dtype=np.int32)
+        h = C.c_void_p()
+        rc = self.lib.mpcgpu_create_multi(C.byref(ps), _ptr(dv), len(dv), C.byref(h))
+        if rc != 0:
+            raise MpcGpuError(f"mpcgpu_create_multi failed ({rc}): {self.lib.mpcgpu_multi_last_error(None).decode()}")
+        self.h = h
+        self.devices = list(map(int, dv))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.mpcgpu_destroy_multi(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_option(self, option: int, value: int):
+        rc = self.lib.mpcgpu_multi_set_option(self.h, int(option), int(value))
+        if rc != 0:
+            raise MpcGpuError(f"mpcgpu_multi_set_option failed ({rc}): {self.lib.mpcgpu_multi_last_error(self.h).decode()}")
+
+    def eval_batch(self, N, Nu, delta, lam, mode="gam"):
+        N = np.ascontiguousarray(np.atleast_1d(N), dtype=np.int32)
+        Nu = np.ascontiguousarray(np.atleast_1d(Nu), dtype=np.int32)
+        n = N.shape[0]
+        delta = np.ascontiguousarray(delta, dtype=np.float64).reshape(n, self.ny)
+        lam = np.ascontiguousarray(lam, dtype=np.float64).reshape(n, self.nu)
+        m = _capi._MODES[mode]
+        cost = np.empty((n, self.ny)) if m == _capi.COST_GAM else np.empty(n)
+        status = np.zeros(n, dtype=np.int32)
+        rc = self.lib.mpcgpu_multi_eval_batch(self.h, n, _ptr(N), _ptr(Nu), _ptr(delta), _ptr(lam), m, _ptr(cost), _ptr(status))
+        if rc != 0:
+            raise MpcGpuError(f"mpcgpu_multi_eval_batch failed ({rc}): {self.lib.mpcgpu_multi_last_error(self.h).decode()}")
+        return {"cost": cost, "status": status}
+
+    def counters(self, device_index: int = 0) -> dict:
+        c = _capi.Counters()
+        self.lib.mpcgpu_multi_get_counters(self.h, int(device_index), C.byref(c))
+        return c.asdict()
+
 
 def measure_fp64_peak(device: int = -1) -> float:
     lib = _capi.load_library()
@@ -176,13 +250,12 @@ def closedloop_toolbox(mpc_toolbox, r, v, N, Nu, delta, lam, nit):
     vv = row2col(v) if ev.nd else None
     if r.shape[0] < nit or r.shape[1] != ev.ny:
         raise MpcGpuError(f"set-point must be {nit} x {ev.ny} (either orientation)")
-    ev.set_signals(r, vv, None, nit)
-    out = ev.eval_batch([int(np.max(N))], [int(np.max(Nu))], np.asarray(delta, float).reshape(1, -1),
-                        np.asarray(lam, float).reshape(1, -1), mode="raw")
-    if out["status"][0] != 0:
-        raise MpcGpuError(f"closed-loop simulation failed with status {int(out['status'][0])}")
+    # one ABI call with per-call signals: the evaluator's own Xsp / mdv / Yref / nit (the tuner state `Par`) stay as they are
+    y, u, ys, uopt, st = ev.closedloop(r, vv, int(np.max(N)), int(np.max(Nu)), delta, lam, nit)
+    if st != 0:
+        raise MpcGpuError(f"closed-loop simulation failed with status {st}")
     t = np.arange(nit)[None, :] * ev.prob.Ts
-    return out["y"][0], out["u"][0], t, out["ys"][0], out["uopt"][0]
+    return y, u, t, ys, uopt
 
 
 def gam_fun(X, par: Evaluator):

@@ -10,11 +10,15 @@ from __future__ import annotations
 import numpy as np
 
 
-def work_estimate(N, Nu, delta, lam):
-    """Relative cost of a candidate: moves and how hard it pushes on the MV limits (same key the library
-    uses to order launches)."""
+def work_estimate(N, Nu, delta, lam, dead_max=None):
+    """Relative cost of a candidate: moves, how hard it pushes on the MV limits, and -- when the plant's longest dead
+    time `dead_max` is given -- the bonus for prediction horizons that barely clear it (those tunings limit-cycle: a
+    QP at every sample).  The same key the library uses to order launches and to deal shards (mpcgpu_work_estimate)."""
     delta = np.abs(np.asarray(delta, float)); lam = np.abs(np.asarray(lam, float))
-    return np.log10(delta.max(axis=1) / (lam.min(axis=1) + 1e-300) + 1e-300) + 0.15 * np.asarray(Nu, float)
+    w = np.log10(delta.max(axis=1) / (lam.min(axis=1) + 1e-300) + 1e-300) + 0.15 * np.asarray(Nu, float)
+    if dead_max is not None:
+        w = w + 2.0 * (np.asarray(N) <= int(dead_max) + 2)
+    return w
 
 
 def shard_indices(n: int, world: int, rank: int, work=None) -> np.ndarray:
@@ -23,7 +27,7 @@ def shard_indices(n: int, world: int, rank: int, work=None) -> np.ndarray:
     return order[rank::world]
 
 
-def evaluate_sharded(evaluate, N, Nu, delta, lam, mode="gam", group=None, device=None):
+def evaluate_sharded(evaluate, N, Nu, delta, lam, mode="gam", group=None, device=None, dead_max=None):
     """evaluate(N, Nu, delta, lam, mode) -> cost array for a shard (an `Evaluator.eval_batch` wrapper).
     Returns the full-population cost on every rank (n x ny for 'gam', n for 'vns').
     `group`: torch.distributed process group (None: default group; not initialised: single rank)."""
@@ -34,10 +38,12 @@ def evaluate_sharded(evaluate, N, Nu, delta, lam, mode="gam", group=None, device
     if not (dist.is_available() and dist.is_initialized()):
         return np.asarray(evaluate(N, Nu, delta, lam, mode))
     world, rank = dist.get_world_size(group), dist.get_rank(group)
-    work = work_estimate(N, Nu, delta, lam)
+    work = work_estimate(N, Nu, delta, lam, dead_max)
+    if device is None and dist.get_backend(group) == "nccl":
+        device = torch.device("cuda", torch.cuda.current_device())
     mine = shard_indices(n, world, rank, work)
     local = np.asarray(evaluate(N[mine], Nu[mine], delta[mine], lam[mine], mode), dtype=np.float64)
-    width = local.shape[1] if local.ndim == 2 else 1
+    width = delta.shape[1] if mode == "gam" else 1   # GAM: one cost per output (ny may be 1); VNS: a scalar
     per = (n + world - 1) // world                     # equal-size slabs for all_gather_into_tensor
     slab = torch.full((per, width), float("nan"), dtype=torch.float64, device=device)
     slab[: len(mine)] = torch.as_tensor(local.reshape(len(mine), width), device=device)
@@ -48,4 +54,4 @@ def evaluate_sharded(evaluate, N, Nu, delta, lam, mode="gam", group=None, device
     for r in range(world):
         idx = shard_indices(n, world, r, work)
         out[idx] = g[r, : len(idx)]
-    return out if width > 1 else out[:, 0]
+    return out if mode == "gam" else out[:, 0]

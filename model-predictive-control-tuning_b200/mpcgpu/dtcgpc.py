@@ -145,6 +145,12 @@ class DtcEvaluator:
         except Exception:
             pass
 
+    def counters(self) -> dict:
+        from . import _capi
+        c = _capi.Counters()
+        self.lib.mpcgpu_dtc_get_counters(self.h, C.byref(c))
+        return c.asdict()
+
     def pack_filters(self, filters):
         """filters: per candidate a list (per output) of (Nr, Dr) -> fr_num, fr_den (n x ny x MAXF), fr_len."""
         n = len(filters)

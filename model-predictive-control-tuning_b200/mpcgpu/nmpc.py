@@ -132,6 +132,12 @@ class NmpcEvaluator:
         except Exception:
             pass
 
+    def counters(self) -> dict:
+        from . import _capi
+        c = _capi.Counters()
+        self.lib.mpcgpu_nmpc_get_counters(self.h, C.byref(c))
+        return c.asdict()
+
     def eval_batch(self, N, Nu, delta, lam, mode="gam", traj=False, r=None):
         """Host arrays in/out.  mode 'raw' | 'gam' | 'vns'; r (ny x nit) overrides the problem's set-point for this call."""
         N = np.ascontiguousarray(np.atleast_1d(N), dtype=np.int32); n = N.shape[0]

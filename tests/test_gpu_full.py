@@ -1,0 +1,127 @@
+"""GPU parity on the populations the benchmark TIMES: every candidate of the 4096-candidate seed-0
+Shell3x3 population (BASELINE.json configs[1]) and every candidate of the 32768-candidate population of the 8-GPU step,
+shard by shard, against the CPU oracle; plus the boundary additions of round 2 (per-call signals, legality option,
+multi-device handle)."""
+import numpy as np
+import pytest
+
+import mpcgpu
+from mpcgpu import shell3x3, synthetic_population, _capi
+from mpcgpu.distributed import shard_indices, work_estimate
+from oracle import oracle as orc
+from oracle import parity
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ev3():
+    e = mpcgpu.Evaluator(shell3x3(2), device=0)
+    yield e
+    e.close()
+
+
+def _check(summ, what, min_strict):
+    assert summ["n_status_nonzero"] == 0, (what, summ)
+    assert summ["n_out_of_tolerance"] == 0, (what, summ)
+    assert summ["max_rel_well_posed"] <= 1e-6, (what, summ)
+    assert summ["frac_le_1e-6"] >= min_strict, (what, summ)
+
+
+def test_every_candidate_of_the_benchmark_population(ev3):
+    """All 4096 candidates bench.py times at N = 1 (seed 0), not a sample of them."""
+    p = ev3.prob
+    op = orc.OracleProblem(p)
+    N, Nu, dl, lm = synthetic_population(p, 4096, seed=0)
+    g0, st0, _ = orc.eval_batch(op, N, Nu, dl, lm, "gam")
+    out = ev3.eval_batch(N, Nu, dl, lm, mode="gam")
+    summ = parity.summary(out["cost"], out["status"], g0, st0, parity.sensitivity(op, N, Nu, dl, lm, "gam", g0))
+    print("parity 4096:", summ)
+    assert summ["n"] == 4096 and summ["n_compared"] == 4096
+    _check(summ, "4096 / seed 0", 0.9)
+
+
+def test_every_shard_of_the_8gpu_population(ev3):
+    """The 8 shards bench.py --gpus 8 times (32768 candidates dealt by estimated work), each evaluated on this GPU."""
+    p = ev3.prob
+    op = orc.OracleProblem(p)
+    N, Nu, dl, lm = synthetic_population(p, 32768, seed=0)
+    g0, st0, _ = orc.eval_batch(op, N, Nu, dl, lm, "gam")
+    sens = parity.sensitivity(op, N, Nu, dl, lm, "gam", g0)
+    work = work_estimate(N, Nu, dl, lm, dead_max=int(p.plant.d.max()))
+    cost = np.empty_like(g0)
+    status = np.empty(len(N), dtype=np.int32)
+    for rank in range(8):
+        idx = shard_indices(len(N), 8, rank, work)
+        assert len(idx) == 4096
+        out = ev3.eval_batch(N[idx], Nu[idx], dl[idx], lm[idx], mode="gam")
+        cost[idx] = out["cost"]; status[idx] = out["status"]
+        _check(parity.summary(out["cost"], out["status"], g0[idx], st0[idx], sens[idx]), f"shard {rank}", 0.9)
+    summ = parity.summary(cost, status, g0, st0, sens)
+    print("parity 32768:", summ)
+    assert summ["n_compared"] == 32768
+
+
+def test_vns_objective_every_candidate_of_a_population(ev3):
+    p = ev3.prob
+    op = orc.OracleProblem(p)
+    N, Nu, dl, lm = synthetic_population(p, 1024, seed=4)
+    f0, st0, _ = orc.eval_batch(op, N, Nu, dl, lm, "vns")
+    out = ev3.eval_batch(N, Nu, dl, lm, mode="vns")
+    summ = parity.summary(out["cost"], out["status"], f0, st0, parity.sensitivity(op, N, Nu, dl, lm, "vns", f0))
+    print("parity vns 1024:", summ)
+    assert summ["n_status_nonzero"] == 0 and summ["n_out_of_tolerance"] == 0, summ
+    assert summ["frac_le_1e-6"] >= 0.5, summ      # the Jnu term (VNS2.m:183-191) divides by |diff(uopt)| ~ 0 for many candidates
+
+
+def test_closedloop_toolbox_leaves_the_tuner_state_alone(ev3):
+    """a closedloop_toolbox call between two GAM evaluations must not change the second one
+    (closedloop_toolbox.m never touches Par.Xsp / Par.Yref; VNS2.m interleaves the two)."""
+    p = ev3.prob
+    N, Nu, dl, lm = synthetic_population(p, 64, seed=11)
+    a = ev3.eval_batch(N, Nu, dl, lm, mode="gam")["cost"]
+    nit_open = 54
+    r_ma = (np.ones((3, nit_open)) * p.L[:, None]) * np.array([[1.0], [0.0], [0.0]])
+    y, u, t, ys, uopt = mpcgpu.closedloop_toolbox(ev3, r_ma, np.zeros((nit_open, 0)), 24, [6, 2, 2], dl[0], lm[0], nit_open)
+    assert y.shape == (3, nit_open) and t.shape == (1, nit_open)
+    b = ev3.eval_batch(N, Nu, dl, lm, mode="gam")["cost"]
+    assert np.array_equal(a, b)
+    v = ev3.eval_batch(N[:8], Nu[:8], dl[:8], lm[:8], mode="vns")["cost"]
+    mpcgpu.closedloop_toolbox(ev3, r_ma, np.zeros((nit_open, 0)), 24, 6, dl[0], lm[0], nit_open)
+    assert np.array_equal(v, ev3.eval_batch(N[:8], Nu[:8], dl[:8], lm[:8], mode="vns")["cost"])
+
+
+def test_vns_legality_option(ev3):
+    """VNS2.m:135  any(N<=dmin) | any(Nu<=1)  inside the library, behind MPCGPU_OPT_VNS_LEGALITY."""
+    p = ev3.prob
+    dmin = np.asarray(p.dmin)
+    N = np.array([int(dmin.max()), int(dmin.max()) + 1, 30, 30], dtype=np.int32)
+    Nu = np.array([2, 2, 1, 2], dtype=np.int32)
+    dl = np.ones((4, 3)); lm = np.ones((4, 3))
+    out = ev3.eval_batch(N, Nu, dl, lm, mode="vns")
+    assert list(out["status"]) == [0, 0, 0, 0]
+    ev3.set_option(_capi.OPT_VNS_LEGALITY, 1)
+    try:
+        out = ev3.eval_batch(N, Nu, dl, lm, mode="vns")
+        assert list(out["status"]) == [4, 0, 4, 0] and np.isnan(out["cost"][[0, 2]]).all() and np.isfinite(out["cost"][[1, 3]]).all()
+        assert [p.valid(int(a), int(b)) for a, b in zip(N, Nu)] == [False, True, False, True]   # same rule as the host mirror
+    finally:
+        ev3.set_option(_capi.OPT_VNS_LEGALITY, 0)
+
+
+@pytest.mark.parametrize("mode", ["gam", "vns"])
+def test_multi_device_handle_matches_single_device_bit_for_bit(ev3, mode):
+    """mpcgpu_create_multi: shards by work, runs the devices concurrently, gathers in population order.  With one GPU in
+    the box the two evaluators share device 0 (the sharding / gather logic is the same); with more, devices 0 and 1."""
+    p = ev3.prob
+    ndev = mpcgpu._capi.load_library().mpcgpu_device_count()
+    devices = [0, 1] if ndev >= 2 else [0, 0]
+    mev = mpcgpu.MultiEvaluator(p, devices=devices)
+    N, Nu, dl, lm = synthetic_population(p, 777, seed=9)     # ragged shards
+    N[5] = 3; Nu[5] = 9                                      # an illegal candidate travels through the gather too
+    a = ev3.eval_batch(N, Nu, dl, lm, mode=mode)
+    b = mev.eval_batch(N, Nu, dl, lm, mode=mode)
+    assert np.array_equal(a["status"], b["status"]) and a["status"][5] == 4
+    assert np.array_equal(a["cost"], b["cost"], equal_nan=True)
+    assert mev.counters(0)["candidates"] > 0 and mev.counters(1)["candidates"] > 0
+    mev.close()
