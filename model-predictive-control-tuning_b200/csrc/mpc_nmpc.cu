@@ -24,6 +24,11 @@
 #include "../../include/mpcgpu.h"
 
 #include "mpc_nmpc_core.h"
+#ifdef NM_GLOBAL_WORK
+#define NM_WORK_ALWAYS 1
+#else
+#define NM_WORK_ALWAYS 0
+#endif
 
 struct NmpcArgs {
     const int *N, *Nu;
@@ -53,7 +58,11 @@ __global__ void __launch_bounds__(NM_THREADS) k_nmpc(const NmpcDev D, int n, int
         return;
     }
     const int sel = mode == 2 ? run : -1;   // VNS: only set-point `sel` is kept, the others are ZEROED (VNS2.m:150-155)
+#ifdef NM_GLOBAL_WORK   /* A/B: the first version's per-run slab in global memory */
+    double *H = A.work + (size_t)item * 2 * NM_LD * NM_LD, *Lc = H + NM_LD * NM_LD;
+#else
     double H[NM_LD * NM_LD], Lc[NM_LD * NM_LD];
+#endif
     unsigned n_calls = 0, n_sqp = 0;
     const int status = nmpc_run(D, p, m, mode, sel, A.delta + (size_t)c * NY, A.lambda + (size_t)c * NU, A.r, A.yref,
                                 A.y ? A.y + (size_t)c * NY * nit : nullptr, A.u ? A.u + (size_t)c * NU * nit : nullptr,
@@ -67,7 +76,7 @@ __global__ void __launch_bounds__(NM_THREADS) k_nmpc(const NmpcDev D, int n, int
 
 
 // =================================================================================================
-// Warp-per-run form of the same algorithm (MPCGPU_NMPC_WARP_PER_RUN=1): lane a owns decision variable a (nz = 2*m <= 32):
+// Warp-per-run form of the same algorithm (the default): lane a owns decision variable a (nz = 2*m <= 32):
 // its plan entry, its column of the sensitivity matrix X = dx/dv, its row of the Gauss-Newton Hessian (in
 // registers) and its gradient entry.  The 3-state rollout and its stage Jacobians are computed redundantly by all
 // lanes (uniform, no divergence); the box-QP is solved cooperatively in shared memory (packed Cholesky of the free
@@ -107,24 +116,68 @@ __device__ __forceinline__ void nmw_argmin(double &v, int &i) {
     i = mi == 0xffffffffu ? -1 : (int)mi;
 }
 
-// predicted cost of the plan in `vs` (shared, nz entries); every lane returns the same value
+// Predicted cost of the plan  clamp(v + alpha d)  for THIS LANE's step length alpha (v, d in shared memory, nz entries):
+// the six step lengths of the backtracking line search are evaluated at once, one per lane group, instead of one rollout
+// after the other (the rollout is a serial chain of RK4 stages; lanes are free).  alpha = 0: the cost of v itself.
 __device__ double w_plan_cost(const NmpcDev &D, const double *x0, const double *uprev, const double *r, int p, int m,
-                              const double *wy2, const double *wu2, const double *vs, int lane) {
+                              const double *wy2, const double *wu2, const double *vs, const double *ds, double alpha) {
     double x[NX] = {x0[0], x0[1], x0[2]};
     double J = 0.0;
+    double up[NU] = {uprev[0], uprev[1]};
     for (int i = 0; i < p; ++i) {
         const int c = i < m ? i : m - 1;
-        const double u[NU] = {vs[NU * c], vs[NU * c + 1]};
+        double u[NU];
+#pragma unroll
+        for (int j = 0; j < NU; ++j) u[j] = fmin(fmax(fma(alpha, ds[NU * c + j], vs[NU * c + j]), D.umin[j]), D.umax[j]);
+        if (i < m) {
+#pragma unroll
+            for (int j = 0; j < NU; ++j) { const double du = u[j] - up[j]; J = fma(wu2[j] * du, du, J); up[j] = u[j]; }
+        }
         rk4_sample(D, x, u, nullptr);
+#pragma unroll
         for (int j = 0; j < NY; ++j) { const double e = r[j] - x[1 + j]; J = fma(wy2[j] * e, e, J); }
     }
-    double part = 0.0;
-    if (lane < NU * m) {
-        const int j = lane % NU;
-        const double du = vs[lane] - (lane < NU ? uprev[j] : vs[lane - NU]);
-        part = wu2[j] * du * du;
+    return J;
+}
+
+// One sample (nsub RK4 steps) with the sensitivities [A|B] = [dx+/dx | dx+/du] (3 x 5) computed LANE-PARALLEL: lane e < 15
+// owns entry (r, c) = (e / 5, e % 5) of every 3 x 5 matrix of the chain (stage sensitivities Dk, the sub-step transition,
+// the running [A|B]); a 3 x 3 by 3 x 5 product is three shuffles and three FMAs per lane instead of 45 serial FMAs.  The
+// state x and the stage derivatives (two exp each) are uniform.  Leaves [A|B] in ABs[0..15) (shared) after a warp barrier.
+__device__ void w_rk4_sens(const NmpcDev &D, double *x, const double *u, int lane, double *ABs) {
+    const int e = lane % 15, r = e / 5, c = e - 5 * r;
+    const double h = D.Ts / D.nsub, diag = r == c ? 1.0 : 0.0;
+    double ABe = diag;
+    for (int s = 0; s < D.nsub; ++s) {
+        double k[4][NX], xs[NX], Jm[15], Dk[4];
+        const double ca[4] = {0.0, 0.5, 0.5, 1.0};
+#pragma unroll
+        for (int st = 0; st < 4; ++st) {
+#pragma unroll
+            for (int i = 0; i < NX; ++i) xs[i] = st == 0 ? x[i] : x[i] + ca[st] * h * k[st - 1][i];
+            vdv_rhs(xs, u, k[st], Jm);
+            // this lane's row of J: entries q < 3 and (for c >= 3) the input column c
+            const double j0 = r == 0 ? Jm[0] : (r == 1 ? Jm[5] : Jm[10]), j1 = r == 0 ? Jm[1] : (r == 1 ? Jm[6] : Jm[11]);
+            const double j2 = r == 0 ? Jm[2] : (r == 1 ? Jm[7] : Jm[12]);
+            const double ju = c == 3 ? (r == 0 ? Jm[3] : (r == 1 ? Jm[8] : Jm[13])) : (c == 4 ? (r == 0 ? Jm[4] : (r == 1 ? Jm[9] : Jm[14])) : 0.0);
+            const double Dxe = (st == 0 ? 0.0 : ca[st] * h * Dk[st - 1]) + diag;   // d xs / d(x_sub, u)
+            double acc = ju;
+            acc = fma(j0, __shfl_sync(NMW_FULL, Dxe, c), acc);
+            acc = fma(j1, __shfl_sync(NMW_FULL, Dxe, 5 + c), acc);
+            acc = fma(j2, __shfl_sync(NMW_FULL, Dxe, 10 + c), acc);
+            Dk[st] = acc;
+        }
+#pragma unroll
+        for (int i = 0; i < NX; ++i) x[i] += (h / 6.0) * (k[0][i] + 2.0 * k[1][i] + 2.0 * k[2][i] + k[3][i]);
+        const double Phie = (h / 6.0) * (Dk[0] + 2.0 * Dk[1] + 2.0 * Dk[2] + Dk[3]) + diag;   // transition of this sub-step
+        double acc = c >= NX ? Phie : 0.0;
+#pragma unroll
+        for (int q = 0; q < NX; ++q) acc = fma(__shfl_sync(NMW_FULL, Phie, 5 * r + q), __shfl_sync(NMW_FULL, ABe, 5 * q + c), acc);
+        ABe = acc;
     }
-    return J + nmw_sum(part);
+    __syncwarp();
+    if (lane < 15) ABs[lane] = ABe;
+    __syncwarp();
 }
 
 // exact  min 1/2 d'Hd + g'd,  lo <= d <= hi  (lo <= 0 <= hi), H SPD in sm.H (leading dimension NMW_LD); result in sm.d
@@ -226,11 +279,13 @@ __device__ int w_nlmpcmove(const NmpcDev &D, const double *x0, const double *upr
     double va = var ? fmin(fmax(sm.v[lane], umn), umx) : 0.0;
     sm.v[lane] = va;
     __syncwarp();
-    double Jcur = w_plan_cost(D, x0, uprev, r, p, m, wy2, wu2, sm.v, lane);
+    sm.d[lane] = 0.0;
+    __syncwarp();
+    double Jcur = w_plan_cost(D, x0, uprev, r, p, m, wy2, wu2, sm.v, sm.d, 0.0);
     int status = 0;
     for (int it = 0; it < D.max_sqp; ++it) {
         *n_sqp += 1;
-        double Hrow[NM_MAXZ], AB[15];
+        double Hrow[NM_MAXZ];
 #pragma unroll
         for (int b = 0; b < NM_MAXZ; ++b) Hrow[b] = 0.0;
         double g = 0.0, X0 = 0.0, X1 = 0.0, X2 = 0.0;
@@ -238,8 +293,9 @@ __device__ int w_nlmpcmove(const NmpcDev &D, const double *x0, const double *upr
         for (int i = 0; i < p; ++i) {
             const int c = i < m ? i : m - 1;
             const double u[NU] = {sm.v[NU * c], sm.v[NU * c + 1]};
-            rk4_sample(D, x, u, AB);
+            w_rk4_sens(D, x, u, lane, sm.t);
             {   // X_a <- A X_a + B e_(c, j)
+                const double *AB = sm.t;
                 const double a0 = X0, a1 = X1, a2 = X2;
                 X0 = AB[0] * a0 + AB[1] * a1 + AB[2] * a2;
                 X1 = AB[5] * a0 + AB[6] * a1 + AB[7] * a2;
@@ -282,18 +338,17 @@ __device__ int w_nlmpcmove(const NmpcDev &D, const double *x0, const double *upr
         const double d = var ? sm.d[lane] : 0.0;
         const double dmax = nmw_max(fabs(d) / sua);
         if (dmax < 1e-10) break;
-        double alpha = 1.0, Jn = 0.0;
-        int acc_ = 0;
-        for (int bt = 0; bt < 6; ++bt) {
-            sm.vt[lane] = var ? fmin(fmax(va + alpha * d, umn), umx) : 0.0;
-            __syncwarp();
-            Jn = w_plan_cost(D, x0, uprev, r, p, m, wy2, wu2, sm.vt, lane);
-            if (Jn < Jcur) { acc_ = 1; break; }
-            alpha *= 0.5;
-            __syncwarp();
-        }
-        if (!acc_) break;
-        va = sm.vt[lane];
+        // ---- backtracking on the true cost: the six step lengths 1, 1/2, .. 1/32 at once, one per lane (lanes >= 6 repeat
+        // the last one); the first (largest) that decreases the cost is taken, as the sequential search would ----
+        const int bt = (lane & 7) < 5 ? (lane & 7) : 5;
+        const double alpha_l = 1.0 / (double)(1 << bt);
+        const double Jl = w_plan_cost(D, x0, uprev, r, p, m, wy2, wu2, sm.v, sm.d, alpha_l);
+        const unsigned okm = __ballot_sync(NMW_FULL, lane < 6 && Jl < Jcur);
+        if (!okm) break;   // no descent at this resolution: converged to rounding
+        const int win = __ffs((int)okm) - 1;
+        const double Jn = __shfl_sync(NMW_FULL, Jl, win);
+        const double alpha = 1.0 / (double)(1 << win);
+        va = var ? fmin(fmax(va + alpha * d, umn), umx) : 0.0;
         __syncwarp();
         sm.v[lane] = va;
         __syncwarp();
@@ -303,12 +358,12 @@ __device__ int w_nlmpcmove(const NmpcDev &D, const double *x0, const double *upr
 }
 
 // mode 0 RAW, 1 GAM, 2 VNS.  One warp per (candidate, run).
-__global__ void __launch_bounds__(32 * NMW_WARPS) k_nmpc_w(const NmpcDev D, int n, int runs, int mode, NmpcArgs A) {
+__global__ void __launch_bounds__(32 * NMW_WARPS) k_nmpc_w(const NmpcDev D, int n, int runs, int mode, const int *order, NmpcArgs A) {
     extern __shared__ double smem_n[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int item = blockIdx.x * NMW_WARPS + warp;
     if (item >= n * runs) return;
-    const int c = item / runs, run = item - c * runs;
+    const int c = order[item / runs], run = item - (item / runs) * runs;   // longest horizons first
     const int p = A.N[c], m = A.Nu[c], nit = D.nit;
     if (p < 2 || p > D.pmax || m < 1 || m > D.mmax || m >= p) {
         if (lane == 0) {
@@ -487,9 +542,10 @@ extern "C" int mpcgpu_nmpc_eval_batch(mpcgpu_nmpc_handle *h, int n, const int32_
     const bool traj = y || u || yopt || uopt || cost_mode == MPCGPU_COST_RAW;
     cudaStream_t s = h->stream;
     const size_t nI = (size_t)n * 4, nT = (size_t)n * 2 * nit;
-    const bool warp_per_run = getenv("MPCGPU_NMPC_WARP_PER_RUN") != nullptr;
+    // default: one warp per run (lane-parallel sensitivities, all line-search steps at once); MPCGPU_NMPC_THREAD_PER_RUN=1: one thread per run
+    const bool warp_per_run = getenv("MPCGPU_NMPC_THREAD_PER_RUN") == nullptr;
     const size_t nD = (size_t)n * (2 * NY + 2 * NU) + (size_t)n * runs + (traj ? 4 * nT : 0) + (size_t)NY * nit +
-                      (warp_per_run ? (size_t)n * runs * 2 * NM_MAXZ * NM_MAXZ : 0) + 8;   // (the thread-per-run kernel keeps H thread-local)
+                      ((warp_per_run || NM_WORK_ALWAYS) ? (size_t)n * runs * 2 * NM_MAXZ * NM_MAXZ : 0) + 8;   // (the thread-per-run kernel keeps H thread-local)
     int *dI = nullptr; double *dD = nullptr;
     if (cudaMalloc((void **)&dI, sizeof(int) * nI) != cudaSuccess || cudaMalloc((void **)&dD, sizeof(double) * nD) != cudaSuccess) {
         cudaFree(dI); h->err = "cudaMalloc failed"; return MPCGPU_ERR_CUDA;
@@ -526,7 +582,7 @@ extern "C" int mpcgpu_nmpc_eval_batch(mpcgpu_nmpc_handle *h, int n, const int32_
         cudaEventRecord(e0, s);
         if (warp_per_run) {   // alternative mapping, same algorithm (measured: no faster, see header)
             const size_t smem = sizeof(double) * NMW_DOUBLES * NMW_WARPS;
-            k_nmpc_w<<<(items + NMW_WARPS - 1) / NMW_WARPS, 32 * NMW_WARPS, smem, s>>>(h->D, n, runs, cost_mode, A);
+            k_nmpc_w<<<(items + NMW_WARPS - 1) / NMW_WARPS, 32 * NMW_WARPS, smem, s>>>(h->D, n, runs, cost_mode, dOrd, A);
         } else {
             k_nmpc<<<(items + NM_THREADS - 1) / NM_THREADS, NM_THREADS, 0, s>>>(h->D, n, runs, cost_mode, dOrd, A);
         }

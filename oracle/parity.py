@@ -12,12 +12,19 @@ from . import oracle as orc
 TOL_COST = 1e-6
 SENS_FACTOR = 10.0
 PERT = (3e-14, -2e-14)
+# the probe is repeated with other ~1e-13 perturbations: a chaotic closed loop (limit cycle against the MV limits) can answer
+# one particular perturbation with a small change by chance; the yard-stick is the largest response
+PERTS = (PERT, (-5e-14, 4e-14), (1e-13, 1e-13))
 
 
-def sensitivity(op, N, Nu, delta, lam, mode, cost_ref, nthreads=0):
-    pert, _, _ = orc.eval_batch(op, N, Nu, np.asarray(delta) * (1 + PERT[0]), np.asarray(lam) * (1 + PERT[1]), mode, nthreads)
-    rel = np.abs(pert - cost_ref) / np.maximum(np.abs(cost_ref), 1e-300)
-    return rel.max(axis=1) if rel.ndim == 2 else rel
+def sensitivity(op, N, Nu, delta, lam, mode, cost_ref, nthreads=0, perts=PERTS):
+    out = None
+    for pd, pl in perts:
+        pert, _, _ = orc.eval_batch(op, N, Nu, np.asarray(delta) * (1 + pd), np.asarray(lam) * (1 + pl), mode, nthreads)
+        rel = np.abs(pert - cost_ref) / np.maximum(np.abs(cost_ref), 1e-300)
+        rel = rel.max(axis=1) if rel.ndim == 2 else rel
+        out = rel if out is None else np.maximum(out, rel)
+    return out
 
 
 def summary(cost, status, cost_ref, status_ref, sens):
@@ -43,5 +50,6 @@ def summary(cost, status, cost_ref, status_ref, sens):
         "n_out_of_tolerance": int(out_of_tol.sum()),
         "n_status_nonzero": int((np.asarray(status) != 0).sum()),
         "n_status_nonzero_oracle": int((np.asarray(status_ref) != 0).sum()),
-        "tolerance": "rel <= max(1e-6, 10 x the oracle's own cost change under a 3e-14 relative perturbation of the weights)",
+        "out_of_tolerance": [(int(c), float(rel[c]), float(tol[c])) for c in np.where(out_of_tol)[0][:8]],
+        "tolerance": "rel <= max(1e-6, 10 x the oracle's own cost change under ~1e-13 relative perturbations of the weights, 3 probes)",
     }

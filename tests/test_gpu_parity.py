@@ -434,13 +434,14 @@ def test_other_plant_shapes(ny, nu, nd, soft):
 
 
 def test_nmpc_warp_per_run_variant(monkeypatch):
-    """The alternative lane mapping of the NMPC kernel (MPCGPU_NMPC_WARP_PER_RUN=1) computes the same thing."""
+    """The two lane mappings of the NMPC kernel (warp per run: the default; MPCGPU_NMPC_THREAD_PER_RUN=1: thread per run)
+    compute the same thing."""
     from mpcgpu.nmpc import vandevusse, NmpcEvaluator
     prob = vandevusse()
     ev = NmpcEvaluator(prob, device=0)
     gold = np.load(os.path.join(ROOT, "tests", "golden", "oracle_golden_nmpc.npz"))
     a = ev.eval_batch(gold["N"], gold["Nu"], gold["delta"], gold["lam"], mode="gam", traj=True)
-    monkeypatch.setenv("MPCGPU_NMPC_WARP_PER_RUN", "1")
+    monkeypatch.setenv("MPCGPU_NMPC_THREAD_PER_RUN", "1")
     b = ev.eval_batch(gold["N"], gold["Nu"], gold["delta"], gold["lam"], mode="gam", traj=True)
     assert (b["status"] == 0).all()
     assert (np.abs(b["y"] - gold["y"]) / prob.sy[None, :, None]).max() < TOL_NMPC_TRAJ
