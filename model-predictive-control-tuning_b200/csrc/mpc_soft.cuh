@@ -23,9 +23,22 @@
 #define SOFT_SYNC() __syncthreads()
 // |d2|^2 is a plain sum of squares here (no cancellation), so linear dependence is tested at the same level as the
 // reference restatement (oracle DEP_TOL); the Schur form of mpc_sim.cuh needs the coarser SIM_DEP_TOL.
-#define SOFT_DEP_TOL 1e-15
+#ifndef SOFT_DEP_TOL
+#define SOFT_DEP_TOL 1e-24   /* far below eps on purpose: see DEP_TOL in the reference restatement (band rows differ by the slack direction only) */
+#endif
+#ifndef SOFT_ITMAX_FACTOR
+#define SOFT_ITMAX_FACTOR 400
+#endif
 #ifndef SOFT_WARM_START
 #define SOFT_WARM_START 0
+#endif
+#ifndef SOFT_REFRESH_ROT
+#define SOFT_REFRESH_ROT 0   /* rotations after which J is rebuilt from H^-1 (cold-start mode).  0 = at every constrained QP: J drifts
+                               under the Givens rotations (cond(H) reaches 1e12 here), and a drifting J made the result depend on
+                               the rounding of the build -- with FMA contraction a well-posed candidate left the oracle's trajectory
+                               by 7e-9 at one sample and by 1e-3 at the end of the run, without it (round 1's -fmad=false) it did
+                               not.  Refreshed at every QP both builds agree with the oracle and with each other (+4 % time;
+                               tools/soft_probe.py, gpurun_out/probe2.log) */
 #endif
 #ifdef MPC_SIMT_EMULATION
 #include <cstdio>
@@ -439,16 +452,16 @@ struct SoftQP {
     // z (shared) in: unconstrained optimum (slack row 0); out: constrained optimum.  0 ok, 1 infeasible, 2 iteration cap.
     __device__ __forceinline__ int solve() {
         int it = 0;
-        const int itmax = 40 * (NU * m + 10);
+        const int itmax = SOFT_ITMAX_FACTOR * (NU * m + 10);
 #if !SOFT_WARM_START
         // Cold start, like the reference restatement: with the band constraints of Shell7x5 several output rows
         // share (almost) one normal -- [0 .. 0, e_i] inside the dead time -- and a carried set that holds two of
         // them makes R nearly singular; the warm-started optimum then loses ~8 digits (measured), the cold one
-        // follows the oracle's pivot sequence.  J J' = H^-1 holds for any rotation of J, so J is kept and only
-        // refreshed from H^-1 after many rotations.
+        // follows the oracle's pivot sequence.  J J' = H^-1 holds for any rotation of J in exact arithmetic; in fp64 it
+        // drifts, so J is refreshed from H^-1 (SOFT_REFRESH_ROT).
         for (int a = q - 1; a >= 0; --a) { set_mask(sm.act[a], false); SOFT_SYNC(); }
         q = 0;
-        if (n_rot > 4 * SIM_REFRESH) { const int rc = factor_init(); if (rc) return rc; }
+        if (n_rot > SOFT_REFRESH_ROT) { const int rc = factor_init(); if (rc) return rc; }
 #else
         if (q > 0 && n_rot > SIM_REFRESH) { const int rc = rebuild(); if (rc) return rc; }
 #endif

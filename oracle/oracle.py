@@ -33,8 +33,23 @@ def build(force: bool = False) -> str:
     return so
 
 
+_ALT = False     # use_alt_build(True): route eval_batch through liboracle_alt.so (same source, different rounding)
+_LIB_ALT = None
+
+
+def use_alt_build(on: bool):
+    global _ALT
+    _ALT = bool(on)
+
+
 def lib():
-    global _LIB
+    global _LIB, _LIB_ALT
+    if _ALT:
+        if _LIB_ALT is None:
+            subprocess.check_call(["make", "-C", _HERE, "-s", "liboracle_alt.so"])
+            _LIB_ALT = C.CDLL(os.path.join(_HERE, "liboracle_alt.so"))
+            _LIB_ALT.orc_cost_vns.restype = C.c_double
+        return _LIB_ALT
     if _LIB is None:
         _LIB = C.CDLL(build())
         _LIB.orc_cost_vns.restype = C.c_double
@@ -79,6 +94,11 @@ def closedloop(op: OracleProblem, N: int, Nu: int, delta, lam, open_loop: bool =
                               uo.ctypes.data_as(C.c_void_p) if open_loop else None,
                               stats.ctypes.data_as(C.c_void_p))
     return y, u, ys, uo, rc, stats
+
+
+def set_pivot_rule(rule: int):
+    """0: most violated constraint first (default); 1: first violated in index order (resolution probe, oracle/parity.py)."""
+    lib().orc_set_pivot_rule(int(rule))
 
 
 def eval_batch(op: OracleProblem, N, Nu, delta, lam, mode: str = "gam", nthreads: int = 0):

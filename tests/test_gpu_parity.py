@@ -242,9 +242,8 @@ def ev75():
 def test_shell7x5_soft_constraint_parity(ev75):
     p = ev75.prob
     op = orc.OracleProblem(p)
-    # lambda in [1e-2, 10] brackets the reference's tuned Shell7x5 result (0.056, 0.0167, 1.61).  Below ~1e-3 the
-    # QP itself degenerates in fp64 (move weights 1e-8 against Weights.ECR = 1e4): the oracle then reports
-    # infeasible / iteration-cap for a third of the candidates, which test_shell7x5_status_codes covers.
+    # lambda in [1e-2, 10] brackets the reference's tuned Shell7x5 result (0.056, 0.0167, 1.61); the survey's full range
+    # (down to 1e-4, cond(H) to 1e12) is test_shell7x5_full_weight_range.
     N, Nu, dl, lm = synthetic_population(p, 48, seed=5, wlo=1e-2)
     g0, st0, stats = orc.eval_batch(op, N, Nu, dl, lm, "gam")
     out = ev75.eval_batch(N, Nu, dl, lm, mode="gam", traj=True)
@@ -268,23 +267,24 @@ def test_shell7x5_soft_constraint_parity(ev75):
     assert c["qp_constrained"] > 0 and c["as_iterations"] > 0
 
 
-def test_shell7x5_status_codes(ev75):
-    """SURVEY.md 8d population (lambda down to 1e-4): a failed QP never aborts the batch -- the candidate gets a
-    non-zero status and a NaN cost (the reference's callers catch the Toolbox's exception and move on,
-    GAM_fun.m:80-91); where both sides succeed the costs agree."""
+def test_shell7x5_full_weight_range(ev75):
+    """SURVEY.md 8d population (lambda log-uniform on [1e-4, 10], delta = 0): every candidate is solved on both sides.
+    Round 1 lost a third of them ("infeasible" / iteration cap) to a dependence test at 1e-15 |d|^2 -- with zero tracking
+    weights the slack direction, all that separates two band rows, is ~1e-15 of |d|^2 at lambda = 1e-4 -- and to an
+    iteration cap of 20 (n + 10); see DEP_TOL in oracle/mpc_oracle.c.  Where fp64 resolves the candidate (the oracle's own
+    cost is stable under 1e-13 perturbations of the weights) the costs agree to 1e-6."""
+    from oracle import parity
     p = ev75.prob
     op = orc.OracleProblem(p)
-    N, Nu, dl, lm = synthetic_population(p, 48, seed=5)
+    N, Nu, dl, lm = synthetic_population(p, 256, seed=5)
     g0, st0, _ = orc.eval_batch(op, N, Nu, dl, lm, "gam")
     out = ev75.eval_batch(N, Nu, dl, lm, mode="gam")
-    bad = out["status"] != 0
-    assert np.isnan(out["cost"][bad]).all() and np.isfinite(out["cost"][~bad]).all()
-    ok = (st0 == 0) & ~bad
-    assert ok.sum() >= 20
-    # here the QPs are degenerate to the point that the pivot sequence decides the 5th digit (DESIGN.md section 2):
-    # most candidates still agree to 1e-6, all of them to 1e-2
-    rel = (np.abs(out["cost"][ok] - g0[ok]) / np.abs(g0[ok])).max(axis=1)
-    assert rel.max() < 1e-2 and (rel < 1e-6).mean() >= 0.5, (rel.max(), (rel < 1e-6).mean())
+    assert (st0 == 0).all() and (out["status"] == 0).all(), (np.bincount(st0), np.bincount(out["status"]))
+    assert np.isfinite(out["cost"]).all()
+    summ = parity.summary(out["cost"], out["status"], g0, st0, parity.sensitivity(op, N, Nu, dl, lm, "gam", g0))
+    print("shell7x5 full range:", summ)
+    assert summ["n_out_of_tolerance"] <= 2, summ            # (the sensitivity probe is a sample, not a bound)
+    assert summ["max_rel_well_posed"] <= 1e-6 and summ["frac_le_1e-6"] >= 0.5, summ
 
 
 def test_shell7x5_vns_and_determinism(ev75):

@@ -9,4 +9,4 @@ for n in [int(a) for a in sys.argv[1:]] or [2048, 16384]:
     ev.eval_batch(*[a[:64] for a in pop], mode="gam")
     out = ev.eval_batch(*pop, mode="gam")
     c = ev.counters()
-    print(os.environ.get("MPCGPU_LIB", "default"), "n", n, "kernel ms", round(c["last_sim_ms"], 1), "cand/s", round(n / c["last_sim_ms"] * 1e3), "status", np.bincount(out["status"]).tolist())
+    print(os.environ.get("MPCGPU_LIB", "default"), "n", n, "kernel ms", round(c["last_sim_ms"], 1), "cand/s", round(n / c["last_sim_ms"] * 1e3), "status", np.bincount(out["status"]).tolist(), c)
