@@ -361,7 +361,7 @@ def run_other(args):
                 "clocks": clk.summary(),
                 "roofline": {"bound": "fp64_fma (serial per-run chains; neither hbm nor tensor)", "achieved": achieved, "peak": fp64_peak,
                              "unit": "TFLOP/s", "frac": achieved / fp64_peak if fp64_peak else None,
-                             "kernel": "k_dtc (warp per candidate)" if args.config == "dtc" else "k_nmpc (thread per run, binned by horizons)",
+                             "kernel": "k_dtc (warp per candidate)" if args.config == "dtc" else "k_nmpc_g<16> (sixteen lanes per run, two runs per warp, sorted by horizons)",
                              "algorithmic_flops_per_launch": fl, "traffic": None,
                              "peak_source": "mpcgpu_measure_fp64_peak, measured live"},
                 "failed_candidates": int((~ok).sum())}

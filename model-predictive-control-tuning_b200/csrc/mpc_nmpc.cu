@@ -2,15 +2,14 @@
 // CSTR (closedloop_toolbox_nmpc.m:36-97, vandevusse_model.m:39-77), GAM / VNS costs fused (GAM_fun.m:110-115,
 // VNS2.m:147-195 nonlinear branch).  C ABI: include/mpcgpu.h, NMPC section.
 //
-// One THREAD per closed-loop run (candidate x VNS run): the work of a run is a long serial chain (59 controller
-// calls, each a few SQP iterations of p*nsub RK4 steps on a 3-state model) with no parallelism worth a warp, and a
-// population supplies tens of thousands of independent runs.  Per controller call (nlmpcmove restated as N1-N4,
+// Default kernel: k_nmpc_g<16> (mpc_nmpc_group.cuh), sixteen lanes per closed-loop run, two runs per warp.  k_nmpc below is the
+// first mapping, one THREAD per run (MPCGPU_NMPC_THREAD_PER_RUN=1), kept for A/B and as the plain statement of the algorithm
+// (it compiles mpc_nmpc_core.h, the source the CPU port shares).  Per controller call (nlmpcmove restated as N1-N4,
 // DESIGN.md section 2 / include/mpcgpu.h):
 //   rollout with forward sensitivities (RK4 stage Jacobians chained: [A|B] per sample, X = dx/dv carried),
 //   Gauss-Newton model  H = sum S'Wy^2 S + D'Wdu^2 D,  g,  accumulated on the fly (S never stored),
 //   exact box-constrained QP step (primal active set on the MV bounds, Cholesky of the free block),
 //   backtracking on the true cost;  stop when the scaled step is < 1e-10.
-// Per-thread state (H: nz^2 <= 900 doubles) lives in local memory, interleaved across the warp by the hardware.
 // HBM traffic per run: 48 B in, 8-16 B out (+ trajectories on request): compute/latency bound, fp64.
 #include <cuda_runtime.h>
 
@@ -75,387 +74,7 @@ __global__ void __launch_bounds__(NM_THREADS) k_nmpc(const NmpcDev D, int n, int
 }
 
 
-// =================================================================================================
-// Warp-per-run form of the same algorithm (the default): lane a owns decision variable a (nz = 2*m <= 32):
-// its plan entry, its column of the sensitivity matrix X = dx/dv, its row of the Gauss-Newton Hessian (in
-// registers) and its gradient entry.  The 3-state rollout and its stage Jacobians are computed redundantly by all
-// lanes (uniform, no divergence); the box-QP is solved cooperatively in shared memory (packed Cholesky of the free
-// block, column-oriented substitutions, warp reductions for the ratio test and the multiplier test).
-// Measured on 16384 Van de Vusse candidates: 1.56 s against 1.47 s for the thread-per-run kernel above -- the run time
-// is the serial chain of RK4 stages (three exp() per right-hand side), which neither mapping shortens; thread-per-run
-// stays the default because it needs no shared memory and packs 32 runs into a warp.
-// =================================================================================================
-#define NMW_WARPS 4
-#define NMW_LD 32
-#define NMW_FULL 0xffffffffu
-#define NMW_DOUBLES (2 * NMW_LD * NMW_LD + 8 * 32)
-
-struct NmwSm { double *H, *Lc, *v, *S, *g, *d, *t, *lo, *hi, *vt; };
-
-__device__ __forceinline__ double nmw_sum(double v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(NMW_FULL, v, o);
-    return v;
-}
-__device__ __forceinline__ double nmw_max(double v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(NMW_FULL, v, o));
-    return v;
-}
-// minimum value over the warp and the smallest lane index holding it (i < 0: lane does not take part)
-__device__ __forceinline__ void nmw_argmin(double &v, int &i) {
-    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
-    const unsigned long long key = (b >> 63) ? ~b : (b | 0x8000000000000000ull);
-    const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
-    const unsigned mhi = __reduce_min_sync(NMW_FULL, i >= 0 ? hi : 0xffffffffu);
-    const unsigned mlo = __reduce_min_sync(NMW_FULL, (i >= 0 && hi == mhi) ? lo : 0xffffffffu);
-    const unsigned mi = __reduce_min_sync(NMW_FULL, (i >= 0 && hi == mhi && lo == mlo) ? (unsigned)i : 0xffffffffu);
-    const unsigned long long mk = ((unsigned long long)mhi << 32) | mlo;
-    const unsigned long long mb = (mk >> 63) ? (mk & 0x7fffffffffffffffull) : ~mk;
-    v = __longlong_as_double((long long)mb);
-    i = mi == 0xffffffffu ? -1 : (int)mi;
-}
-
-// Predicted cost of the plan  clamp(v + alpha d)  for THIS LANE's step length alpha (v, d in shared memory, nz entries):
-// the six step lengths of the backtracking line search are evaluated at once, one per lane group, instead of one rollout
-// after the other (the rollout is a serial chain of RK4 stages; lanes are free).  alpha = 0: the cost of v itself.
-__device__ double w_plan_cost(const NmpcDev &D, const double *x0, const double *uprev, const double *r, int p, int m,
-                              const double *wy2, const double *wu2, const double *vs, const double *ds, double alpha) {
-    double x[NX] = {x0[0], x0[1], x0[2]};
-    double J = 0.0;
-    double up[NU] = {uprev[0], uprev[1]};
-    for (int i = 0; i < p; ++i) {
-        const int c = i < m ? i : m - 1;
-        double u[NU];
-#pragma unroll
-        for (int j = 0; j < NU; ++j) u[j] = fmin(fmax(fma(alpha, ds[NU * c + j], vs[NU * c + j]), D.umin[j]), D.umax[j]);
-        if (i < m) {
-#pragma unroll
-            for (int j = 0; j < NU; ++j) { const double du = u[j] - up[j]; J = fma(wu2[j] * du, du, J); up[j] = u[j]; }
-        }
-        rk4_sample(D, x, u, nullptr);
-#pragma unroll
-        for (int j = 0; j < NY; ++j) { const double e = r[j] - x[1 + j]; J = fma(wy2[j] * e, e, J); }
-    }
-    return J;
-}
-
-// One sample (nsub RK4 steps) with the sensitivities [A|B] = [dx+/dx | dx+/du] (3 x 5) computed LANE-PARALLEL: lane e < 15
-// owns entry (r, c) = (e / 5, e % 5) of every 3 x 5 matrix of the chain (stage sensitivities Dk, the sub-step transition,
-// the running [A|B]); a 3 x 3 by 3 x 5 product is three shuffles and three FMAs per lane instead of 45 serial FMAs.  The
-// state x and the stage derivatives (two exp each) are uniform.  Leaves [A|B] in ABs[0..15) (shared) after a warp barrier.
-__device__ void w_rk4_sens(const NmpcDev &D, double *x, const double *u, int lane, double *ABs) {
-    const int e = lane % 15, r = e / 5, c = e - 5 * r;
-    const double h = D.Ts / D.nsub, diag = r == c ? 1.0 : 0.0;
-    double ABe = diag;
-    for (int s = 0; s < D.nsub; ++s) {
-        double k[4][NX], xs[NX], Jm[15], Dk[4];
-        const double ca[4] = {0.0, 0.5, 0.5, 1.0};
-#pragma unroll
-        for (int st = 0; st < 4; ++st) {
-#pragma unroll
-            for (int i = 0; i < NX; ++i) xs[i] = st == 0 ? x[i] : x[i] + ca[st] * h * k[st - 1][i];
-            vdv_rhs(xs, u, k[st], Jm);
-            // this lane's row of J: entries q < 3 and (for c >= 3) the input column c
-            const double j0 = r == 0 ? Jm[0] : (r == 1 ? Jm[5] : Jm[10]), j1 = r == 0 ? Jm[1] : (r == 1 ? Jm[6] : Jm[11]);
-            const double j2 = r == 0 ? Jm[2] : (r == 1 ? Jm[7] : Jm[12]);
-            const double ju = c == 3 ? (r == 0 ? Jm[3] : (r == 1 ? Jm[8] : Jm[13])) : (c == 4 ? (r == 0 ? Jm[4] : (r == 1 ? Jm[9] : Jm[14])) : 0.0);
-            const double Dxe = (st == 0 ? 0.0 : ca[st] * h * Dk[st - 1]) + diag;   // d xs / d(x_sub, u)
-            double acc = ju;
-            acc = fma(j0, __shfl_sync(NMW_FULL, Dxe, c), acc);
-            acc = fma(j1, __shfl_sync(NMW_FULL, Dxe, 5 + c), acc);
-            acc = fma(j2, __shfl_sync(NMW_FULL, Dxe, 10 + c), acc);
-            Dk[st] = acc;
-        }
-#pragma unroll
-        for (int i = 0; i < NX; ++i) x[i] += (h / 6.0) * (k[0][i] + 2.0 * k[1][i] + 2.0 * k[2][i] + k[3][i]);
-        const double Phie = (h / 6.0) * (Dk[0] + 2.0 * Dk[1] + 2.0 * Dk[2] + Dk[3]) + diag;   // transition of this sub-step
-        double acc = c >= NX ? Phie : 0.0;
-#pragma unroll
-        for (int q = 0; q < NX; ++q) acc = fma(__shfl_sync(NMW_FULL, Phie, 5 * r + q), __shfl_sync(NMW_FULL, ABe, 5 * q + c), acc);
-        ABe = acc;
-    }
-    __syncwarp();
-    if (lane < 15) ABs[lane] = ABe;
-    __syncwarp();
-}
-
-// exact  min 1/2 d'Hd + g'd,  lo <= d <= hi  (lo <= 0 <= hi), H SPD in sm.H (leading dimension NMW_LD); result in sm.d
-__device__ int w_box_qp(int nz, const NmwSm &sm, int lane) {
-    const bool var = lane < nz;
-    const double ga = var ? sm.g[lane] : 0.0, loa = var ? sm.lo[lane] : 0.0, hia = var ? sm.hi[lane] : 0.0;
-    int fixed = !var ? 2 : ((ga > 0.0 && loa >= 0.0) ? -1 : ((ga < 0.0 && hia <= 0.0) ? 1 : 0));
-    double da = 0.0;
-    const double gscale = nmw_max(fabs(ga));
-    for (int it = 0; it < 6 * nz + 20; ++it) {
-        sm.d[lane] = da;
-        const unsigned fmask = __ballot_sync(NMW_FULL, fixed == 0);
-        const int nf = __popc(fmask), fi = __popc(fmask & ((1u << lane) - 1u));
-        __syncwarp();
-        if (fixed == 0) {
-            // packed row fi of H_FF and the right-hand side -(g_F + H_FA d_A)
-            double rhs = -ga;
-            int fj = 0;
-            for (int b = 0; b < nz; ++b) {
-                const double hab = sm.H[lane * NMW_LD + b];
-                if ((fmask >> b) & 1u) { if (fj <= fi) sm.Lc[fi * NMW_LD + fj] = hab; fj++; }
-                else rhs = fma(-hab, sm.d[b], rhs);
-            }
-            sm.t[fi] = rhs;
-        }
-        __syncwarp();
-        // Cholesky of the packed block, lanes = rows
-        for (int k = 0; k < nf; ++k) {
-            const double dkk = sm.Lc[k * NMW_LD + k];
-            if (!(dkk > 0.0)) return 3;
-            const double ckk = sqrt(dkk);
-            double lrk = 0.0;
-            if (lane >= k && lane < nf) { lrk = lane == k ? ckk : sm.Lc[lane * NMW_LD + k] / ckk; sm.Lc[lane * NMW_LD + k] = lrk; }
-            __syncwarp();
-            if (lane > k && lane < nf)
-                for (int c = k + 1; c <= lane; ++c) sm.Lc[lane * NMW_LD + c] = fma(-lrk, sm.Lc[c * NMW_LD + k], sm.Lc[lane * NMW_LD + c]);
-            __syncwarp();
-        }
-        for (int k = 0; k < nf; ++k) {   // L y = t
-            const double yk = sm.t[k] / sm.Lc[k * NMW_LD + k];
-            __syncwarp();
-            if (lane == k) sm.t[k] = yk;
-            else if (lane > k && lane < nf) sm.t[lane] = fma(-sm.Lc[lane * NMW_LD + k], yk, sm.t[lane]);
-            __syncwarp();
-        }
-        for (int k = nf - 1; k >= 0; --k) {   // L' x = y
-            const double xk = sm.t[k] / sm.Lc[k * NMW_LD + k];
-            __syncwarp();
-            if (lane == k) sm.t[k] = xk;
-            else if (lane < k) sm.t[lane] = fma(-sm.Lc[k * NMW_LD + lane], xk, sm.t[lane]);
-            __syncwarp();
-        }
-        // longest feasible step toward the Newton point of the face
-        double alpha = 1.0;
-        int blk = -1, side = 0;
-        double step = 0.0;
-        if (fixed == 0) {
-            step = sm.t[fi] - da;
-            if (step > 0.0 && da + step > hia) { alpha = (hia - da) / step; blk = lane; side = 1; }
-            if (step < 0.0 && da + step < loa) { alpha = (loa - da) / step; blk = lane; side = -1; }
-        }
-        double amin = alpha;
-        int bl = blk;
-        nmw_argmin(amin, bl);
-        if (bl < 0) amin = 1.0;
-        if (fixed == 0) da += amin * step;
-        if (bl >= 0) {
-            if (lane == bl) { da = side > 0 ? hia : loa; fixed = side; }
-            continue;
-        }
-        // minimiser of the face: release the bound with the most wrong-signed multiplier
-        sm.d[lane] = da;
-        __syncwarp();
-        double viol = 0.0;
-        int cand = -1;
-        if (fixed == 1 || fixed == -1) {
-            double gi = ga;
-            for (int b = 0; b < nz; ++b) gi = fma(sm.H[lane * NMW_LD + b], sm.d[b], gi);
-            viol = fixed < 0 ? -gi : gi;
-            if (viol > 0.0) cand = lane;
-        }
-        double key = -viol;
-        nmw_argmin(key, cand);
-        if (cand < 0 || -key <= 1e-14 * gscale) { sm.d[lane] = da; __syncwarp(); return 0; }
-        if (lane == cand) fixed = 0;
-    }
-    sm.d[lane] = da;
-    __syncwarp();
-    return 2;
-}
-
-// one nlmpcmove by one warp: plan in sm.v (in: start, out: optimum)
-__device__ int w_nlmpcmove(const NmpcDev &D, const double *x0, const double *uprev, const double *r, int p, int m,
-                           const double *wy2, const double *wu2, const NmwSm &sm, int lane, unsigned *n_sqp) {
-    const int nz = NU * m;
-    const bool var = lane < nz;
-    const int ja = lane % NU, ca = lane / NU;
-    const double umn = D.umin[ja], umx = D.umax[ja], sua = D.su[ja];
-    double va = var ? fmin(fmax(sm.v[lane], umn), umx) : 0.0;
-    sm.v[lane] = va;
-    __syncwarp();
-    sm.d[lane] = 0.0;
-    __syncwarp();
-    double Jcur = w_plan_cost(D, x0, uprev, r, p, m, wy2, wu2, sm.v, sm.d, 0.0);
-    int status = 0;
-    for (int it = 0; it < D.max_sqp; ++it) {
-        *n_sqp += 1;
-        double Hrow[NM_MAXZ];
-#pragma unroll
-        for (int b = 0; b < NM_MAXZ; ++b) Hrow[b] = 0.0;
-        double g = 0.0, X0 = 0.0, X1 = 0.0, X2 = 0.0;
-        double x[NX] = {x0[0], x0[1], x0[2]};
-        for (int i = 0; i < p; ++i) {
-            const int c = i < m ? i : m - 1;
-            const double u[NU] = {sm.v[NU * c], sm.v[NU * c + 1]};
-            w_rk4_sens(D, x, u, lane, sm.t);
-            {   // X_a <- A X_a + B e_(c, j)
-                const double *AB = sm.t;
-                const double a0 = X0, a1 = X1, a2 = X2;
-                X0 = AB[0] * a0 + AB[1] * a1 + AB[2] * a2;
-                X1 = AB[5] * a0 + AB[6] * a1 + AB[7] * a2;
-                X2 = AB[10] * a0 + AB[11] * a1 + AB[12] * a2;
-                if (var && ca == c) { X0 += AB[NX + ja]; X1 += AB[5 + NX + ja]; X2 += AB[10 + NX + ja]; }
-            }
-#pragma unroll
-            for (int j = 0; j < NY; ++j) {
-                const double Sa = var ? (j == 0 ? X1 : X2) : 0.0;   // dy_j/dv_a
-                sm.S[lane] = Sa;
-                __syncwarp();
-                const double e = r[j] - x[1 + j];
-                const double wa = wy2[j] * Sa;
-                g = fma(-wa, e, g);
-#pragma unroll
-                for (int b = 0; b < NM_MAXZ; ++b) Hrow[b] = fma(wa, sm.S[b], Hrow[b]);
-                __syncwarp();
-            }
-        }
-        // move-suppression terms (lane-local rows of D'Wdu^2 D)
-        if (var) {
-            const double w = wu2[ja];
-            const double du = va - (ca == 0 ? uprev[ja] : sm.v[lane - NU]);
-            g = fma(w, du, g);
-            const bool has_next = ca + 1 < m;
-            if (has_next) g = fma(-w, sm.v[lane + NU] - va, g);
-#pragma unroll
-            for (int b = 0; b < NM_MAXZ; ++b) {
-                if (b == lane) Hrow[b] += has_next ? 2.0 * w : w;
-                if (b + NU == lane) Hrow[b] -= w;
-                if (b == lane + NU && has_next) Hrow[b] -= w;
-            }
-        }
-#pragma unroll
-        for (int b = 0; b < NM_MAXZ; ++b) sm.H[lane * NMW_LD + b] = Hrow[b];
-        sm.g[lane] = g; sm.lo[lane] = umn - va; sm.hi[lane] = umx - va;
-        __syncwarp();
-        const int rc = w_box_qp(nz, sm, lane);
-        if (rc) { status = rc; break; }
-        const double d = var ? sm.d[lane] : 0.0;
-        const double dmax = nmw_max(fabs(d) / sua);
-        if (dmax < 1e-10) break;
-        // ---- backtracking on the true cost: the six step lengths 1, 1/2, .. 1/32 at once, one per lane (lanes >= 6 repeat
-        // the last one); the first (largest) that decreases the cost is taken, as the sequential search would ----
-        const int bt = (lane & 7) < 5 ? (lane & 7) : 5;
-        const double alpha_l = 1.0 / (double)(1 << bt);
-        const double Jl = w_plan_cost(D, x0, uprev, r, p, m, wy2, wu2, sm.v, sm.d, alpha_l);
-        const unsigned okm = __ballot_sync(NMW_FULL, lane < 6 && Jl < Jcur);
-        if (!okm) break;   // no descent at this resolution: converged to rounding
-        const int win = __ffs((int)okm) - 1;
-        const double Jn = __shfl_sync(NMW_FULL, Jl, win);
-        const double alpha = 1.0 / (double)(1 << win);
-        va = var ? fmin(fmax(va + alpha * d, umn), umx) : 0.0;
-        __syncwarp();
-        sm.v[lane] = va;
-        __syncwarp();
-        Jcur = Jn;
-    }
-    return status;
-}
-
-// mode 0 RAW, 1 GAM, 2 VNS.  One warp per (candidate, run).
-__global__ void __launch_bounds__(32 * NMW_WARPS) k_nmpc_w(const NmpcDev D, int n, int runs, int mode, const int *order, NmpcArgs A) {
-    extern __shared__ double smem_n[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int item = blockIdx.x * NMW_WARPS + warp;
-    if (item >= n * runs) return;
-    const int c = order[item / runs], run = item - (item / runs) * runs;   // longest horizons first
-    const int p = A.N[c], m = A.Nu[c], nit = D.nit;
-    if (p < 2 || p > D.pmax || m < 1 || m > D.mmax || m >= p) {
-        if (lane == 0) {
-            A.status[c] = MPCGPU_CAND_INVALID;
-            if (mode == 1) for (int j = 0; j < NY; ++j) A.cost[(size_t)c * NY + j] = NAN;
-            if (mode == 2) A.part[(size_t)c * runs + run] = NAN;
-        }
-        return;
-    }
-    NmwSm sm;
-    {
-        double *q_ = smem_n + (size_t)warp * NMW_DOUBLES;
-        sm.H = q_; q_ += NMW_LD * NMW_LD; sm.Lc = q_; q_ += NMW_LD * NMW_LD;
-        sm.v = q_; q_ += 32; sm.S = q_; q_ += 32; sm.g = q_; q_ += 32; sm.d = q_; q_ += 32; sm.t = q_; q_ += 32;
-        sm.lo = q_; q_ += 32; sm.hi = q_; q_ += 32; sm.vt = q_;
-    }
-    const int sel = mode == 2 ? run : -1;
-    double wy2[NY], wu2[NU];
-    for (int j = 0; j < NY; ++j) { const double w = A.delta[(size_t)c * NY + j] / D.sy[j]; wy2[j] = w * w; }
-    for (int j = 0; j < NU; ++j) { const double w = A.lambda[(size_t)c * NU + j] / D.su[j]; wu2[j] = w * w; }
-    double rr[NY];
-    auto ref_at = [&](int k, double *out) {
-        for (int j = 0; j < NY; ++j) out[j] = (sel < 0 || sel == j) ? A.r[(size_t)j * nit + k] : 0.0;
-    };
-    unsigned n_sqp = 0, n_calls = 0;
-    int status = 0;
-    const bool want_ol = mode != 1 || A.yopt || A.uopt;
-    double jnu = 0.0, cost_acc[NY] = {0.0, 0.0}, vns_acc = 0.0;
-    double xo[NX] = {D.x0[0], D.x0[1], D.x0[2]};
-    double vopt_a = 0.0;   // lane a: entry a of the open-loop plan
-    if (want_ol) {
-        sm.v[lane] = D.u0[lane % NU];
-        __syncwarp();
-        ref_at(nit - 1, rr);
-        const int rc = w_nlmpcmove(D, D.x0, D.u0, rr, p, m, wy2, wu2, sm, lane, &n_sqp);
-        n_calls++;
-        if (rc) status = rc;
-        vopt_a = sm.v[lane];
-        if (mode == 2) {   // Jnu (VNS2.m:183-191) on input `sel`
-            const int j = sel;
-            const double u0a = fabs(sm.v[j]);
-            for (int cc = 0; cc + 1 < m && cc + 1 < nit; ++cc) {
-                const double xn = u0a / fabs(sm.v[NU * (cc + 1) + j] - sm.v[NU * cc + j]);
-                if (fabs(xn) <= 1.7976931348623157e308) jnu += xn * xn;
-            }
-        }
-        __syncwarp();
-    }
-    double x[NX] = {D.x0[0], D.x0[1], D.x0[2]}, uprev[NU] = {D.u0[0], D.u0[1]};
-    sm.v[lane] = D.u0[lane % NU];
-    __syncwarp();
-    for (int k = 0; k < nit; ++k) {
-        double uo[NU] = {0.0, 0.0};
-        if (want_ol) {
-            const int cc = k < m ? k : m - 1;
-            uo[0] = __shfl_sync(NMW_FULL, vopt_a, NU * cc);
-            uo[1] = __shfl_sync(NMW_FULL, vopt_a, NU * cc + 1);
-        }
-        if (k > 0) {
-            ref_at(k, rr);
-            const int rc = w_nlmpcmove(D, x, uprev, rr, p, m, wy2, wu2, sm, lane, &n_sqp);   // warm start = previous plan
-            n_calls++;
-            if (rc) status = rc;
-            uprev[0] = sm.v[0]; uprev[1] = sm.v[1];
-            rk4_sample(D, x, uprev, nullptr);
-            for (int i = 0; i < NX; ++i)
-                if (x[i] < D.xmin[i] - 1e-9 || x[i] > D.xmax[i] + 1e-9) { if (!status) status = 5; }
-            if (want_ol) rk4_sample(D, xo, uo, nullptr);
-        }
-        for (int j = 0; j < NY; ++j) {
-            const bool mine = sel < 0 || sel == j;
-            const double yj = x[1 + j], yoj = xo[1 + j], yr = A.yref[(size_t)j * nit + k];
-            if (mine) {
-                if (lane == 0) {
-                    if (A.y) A.y[((size_t)c * NY + j) * nit + k] = yj;
-                    if (A.u) A.u[((size_t)c * NU + j) * nit + k] = uprev[j];
-                    if (want_ol && A.yopt) A.yopt[((size_t)c * NY + j) * nit + k] = yoj;
-                    if (want_ol && A.uopt) A.uopt[((size_t)c * NU + j) * nit + k] = uo[j];
-                }
-                if (mode == 1) cost_acc[j] += (yj - yr) * (yj - yr);
-                if (mode == 2 && k >= D.inK - 1) vns_acc += (yj - yoj) * (yj - yoj) + (yj - yr) * (yj - yr);
-            }
-        }
-    }
-    if (lane == 0) {
-        if (mode == 1) for (int j = 0; j < NY; ++j) A.cost[(size_t)c * NY + j] = (status == 0 || status == 5) ? cost_acc[j] : NAN;
-        if (mode == 2) A.part[(size_t)c * runs + run] = (status == 0 || status == 5) ? vns_acc + jnu : NAN;
-        if (status) atomicMax(A.status + c, status);
-        atomicAdd(A.counters + 0, (unsigned long long)n_calls);
-        atomicAdd(A.counters + 1, (unsigned long long)n_sqp);
-    }
-}
+#include "mpc_nmpc_group.cuh"
 
 __global__ void k_nmpc_finish(int n, int runs, const int *N, const double *part, const int *status, double *cost) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -525,7 +144,9 @@ extern "C" int mpcgpu_nmpc_create(const mpcgpu_nmpc_problem *pb, int device, mpc
     if ((ce = cudaMalloc((void **)&h->dYref, nb)) != cudaSuccess) return fail("alloc", ce);
     cudaMemcpy(h->dR, h->r.data(), nb, cudaMemcpyHostToDevice);
     if ((ce = cudaMemcpy(h->dYref, h->yref.data(), nb, cudaMemcpyHostToDevice)) != cudaSuccess) return fail("copy", ce);
-    cudaFuncSetAttribute(k_nmpc_w, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * NMW_DOUBLES * NMW_WARPS));
+    cudaFuncSetAttribute(k_nmpc_g<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * nmg_doubles(NM_MAXZ) * 4));
+    cudaFuncSetAttribute(k_nmpc_g<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * nmg_doubles(NM_MAXZ) * 2));
+    cudaFuncSetAttribute(k_nmpc_g<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * nmg_doubles(NM_MAXZ)));
     *out = h;
     return MPCGPU_OK;
 }
@@ -542,19 +163,24 @@ extern "C" int mpcgpu_nmpc_eval_batch(mpcgpu_nmpc_handle *h, int n, const int32_
     const bool traj = y || u || yopt || uopt || cost_mode == MPCGPU_COST_RAW;
     cudaStream_t s = h->stream;
     const size_t nI = (size_t)n * 4, nT = (size_t)n * 2 * nit;
-    // default: one warp per run (lane-parallel sensitivities, all line-search steps at once); MPCGPU_NMPC_THREAD_PER_RUN=1: one thread per run
-    const bool warp_per_run = getenv("MPCGPU_NMPC_THREAD_PER_RUN") == nullptr;
+    // default: sixteen lanes per run, two runs per warp (mpc_nmpc_group.cuh); MPCGPU_NMPC_GROUP=8|32 for A/B (measured, 2048 / 16384
+    // candidates: G = 8 286 / 545 ms, G = 16 231 / 510 ms, G = 32 237 / -- ms); MPCGPU_NMPC_THREAD_PER_RUN=1: one thread per run (1.6 s)
+    const bool grouped = getenv("MPCGPU_NMPC_THREAD_PER_RUN") == nullptr;
+    const int G = getenv("MPCGPU_NMPC_GROUP") ? atoi(getenv("MPCGPU_NMPC_GROUP")) : 16;
     const size_t nD = (size_t)n * (2 * NY + 2 * NU) + (size_t)n * runs + (traj ? 4 * nT : 0) + (size_t)NY * nit +
-                      ((warp_per_run || NM_WORK_ALWAYS) ? (size_t)n * runs * 2 * NM_MAXZ * NM_MAXZ : 0) + 8;   // (the thread-per-run kernel keeps H thread-local)
+                      (NM_WORK_ALWAYS ? (size_t)n * runs * 2 * NM_MAXZ * NM_MAXZ : 0) + 8;
     int *dI = nullptr; double *dD = nullptr;
     if (cudaMalloc((void **)&dI, sizeof(int) * nI) != cudaSuccess || cudaMalloc((void **)&dD, sizeof(double) * nD) != cudaSuccess) {
         cudaFree(dI); h->err = "cudaMalloc failed"; return MPCGPU_ERR_CUDA;
     }
     int *dN = dI, *dNu = dN + n, *dSt = dNu + n, *dOrd = dSt + n;
-    // candidates binned by (Nu, N): the 32 runs of a warp then share their loop trip counts
+    // candidates binned by horizons, longest first: the runs of a warp then share their loop trip counts (thread per run: by
+    // (Nu, N), the box-QP dominates its divergence; grouped: by (N, Nu), the rollout length is what the groups of a warp share)
     std::vector<int> order(n);
     for (int c = 0; c < n; ++c) order[c] = c;
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return Nu[a] != Nu[b] ? Nu[a] > Nu[b] : N[a] > N[b]; });
+    if (grouped) std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return N[a] != N[b] ? N[a] > N[b] : Nu[a] > Nu[b]; });
+    int maxnu = 1;
+    for (int c = 0; c < n; ++c) if (Nu[c] >= 1 && Nu[c] <= NM_MAXM && Nu[c] > maxnu) maxnu = Nu[c];
     double *q_ = dD;
     double *dDl = q_; q_ += (size_t)n * NY; double *dLm = q_; q_ += (size_t)n * NU;
     double *dCost = q_; q_ += (size_t)n * NY; double *dPart = q_; q_ += (size_t)n * runs;
@@ -580,9 +206,17 @@ extern "C" int mpcgpu_nmpc_eval_batch(mpcgpu_nmpc_handle *h, int n, const int32_
         cudaEvent_t e0 = nullptr, e1 = nullptr;
         cudaEventCreate(&e0); cudaEventCreate(&e1);
         cudaEventRecord(e0, s);
-        if (warp_per_run) {   // alternative mapping, same algorithm (measured: no faster, see header)
-            const size_t smem = sizeof(double) * NMW_DOUBLES * NMW_WARPS;
-            k_nmpc_w<<<(items + NMW_WARPS - 1) / NMW_WARPS, 32 * NMW_WARPS, smem, s>>>(h->D, n, runs, cost_mode, dOrd, A);
+        if (grouped) {
+            // shared memory for the largest plan of THIS population (9.6 KB per run at Nu = 15).  Binning the population by
+            // control horizon into launches with less shared memory each (more resident warps) was measured and dropped:
+            // 810 vs 800 ms for 16384 candidates -- the time is the latency of the runs, not their residency (gpurun_out/nmpc3.log)
+            const int rpw = G == 32 ? 1 : (G == 8 ? 4 : 2);   // runs per warp
+            const int maxz = NU * maxnu;
+            const size_t smem = sizeof(double) * nmg_doubles(maxz) * rpw;
+            const int grid = (items + rpw - 1) / rpw;
+            if (rpw == 1) k_nmpc_g<32><<<grid, 32, smem, s>>>(h->D, 0, items, runs, cost_mode, dOrd, A, maxz);
+            else if (rpw == 2) k_nmpc_g<16><<<grid, 32, smem, s>>>(h->D, 0, items, runs, cost_mode, dOrd, A, maxz);
+            else k_nmpc_g<8><<<grid, 32, smem, s>>>(h->D, 0, items, runs, cost_mode, dOrd, A, maxz);
         } else {
             k_nmpc<<<(items + NM_THREADS - 1) / NM_THREADS, NM_THREADS, 0, s>>>(h->D, n, runs, cost_mode, dOrd, A);
         }

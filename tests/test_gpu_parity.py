@@ -433,14 +433,18 @@ def test_other_plant_shapes(ny, nu, nd, soft):
     ev.close()
 
 
-def test_nmpc_warp_per_run_variant(monkeypatch):
-    """The two lane mappings of the NMPC kernel (warp per run: the default; MPCGPU_NMPC_THREAD_PER_RUN=1: thread per run)
+def test_nmpc_lane_mappings(monkeypatch):
+    """The lane mappings of the NMPC kernel (a group of 16 lanes per run: the default; MPCGPU_NMPC_GROUP=8: eight; MPCGPU_NMPC_THREAD_PER_RUN=1: thread per run)
     compute the same thing."""
     from mpcgpu.nmpc import vandevusse, NmpcEvaluator
     prob = vandevusse()
     ev = NmpcEvaluator(prob, device=0)
     gold = np.load(os.path.join(ROOT, "tests", "golden", "oracle_golden_nmpc.npz"))
     a = ev.eval_batch(gold["N"], gold["Nu"], gold["delta"], gold["lam"], mode="gam", traj=True)
+    monkeypatch.setenv("MPCGPU_NMPC_GROUP", "8")
+    g8 = ev.eval_batch(gold["N"], gold["Nu"], gold["delta"], gold["lam"], mode="gam", traj=True)
+    assert (g8["status"] == 0).all() and (np.abs(a["u"] - g8["u"]) / prob.su[None, :, None]).max() < 1e-6
+    monkeypatch.delenv("MPCGPU_NMPC_GROUP")
     monkeypatch.setenv("MPCGPU_NMPC_THREAD_PER_RUN", "1")
     b = ev.eval_batch(gold["N"], gold["Nu"], gold["delta"], gold["lam"], mode="gam", traj=True)
     assert (b["status"] == 0).all()
