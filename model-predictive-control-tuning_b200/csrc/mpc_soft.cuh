@@ -30,7 +30,12 @@
 #define SOFT_ITMAX_FACTOR 400
 #endif
 #ifndef SOFT_WARM_START
-#define SOFT_WARM_START 0
+#define SOFT_WARM_START 0   /* 1: carry the active set across samples.  Measured (round 2, tools/soft_probe.py, gpurun_out/probe4.log, probe5.log):
+                               2.6 x fewer iterations and 2.6 x less time (203 vs 541 ms for 256 full-range candidates), but 70 of 256
+                               candidates that the oracle resolves to 1e-7 then differ by more than 1e-6, with or without a rebuild
+                               of the carried factor at every QP: the degenerate band rows (equal normals inside the dead time)
+                               make the multipliers of a carried set non-unique, and the shed / re-add sequence ends on another
+                               vertex of the same face within VIOL_TOL.  Off: parity first. */
 #endif
 #ifndef SOFT_REFRESH_ROT
 #define SOFT_REFRESH_ROT 0   /* rotations after which J is rebuilt from H^-1 (cold-start mode).  0 = at every constrained QP: J drifts
@@ -463,7 +468,7 @@ struct SoftQP {
         q = 0;
         if (n_rot > SOFT_REFRESH_ROT) { const int rc = factor_init(); if (rc) return rc; }
 #else
-        if (q > 0 && n_rot > SIM_REFRESH) { const int rc = rebuild(); if (rc) return rc; }
+        if (n_rot > SOFT_REFRESH_ROT) { const int rc = q > 0 ? rebuild() : factor_init(); if (rc) return rc; }
 #endif
         // ---- warm start on the carried set: mu = R^-1 R^-T (b_A - N_A' z_unc), shed negative multipliers ----
         while (q > 0) {

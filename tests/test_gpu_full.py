@@ -132,3 +132,39 @@ def test_multi_device_handle_matches_single_device_bit_for_bit(ev3, mode):
     assert np.array_equal(a["cost"], b["cost"], equal_nan=True)
     assert mev.counters(0)["candidates"] > 0 and mev.counters(1)["candidates"] > 0
     mev.close()
+
+
+def test_gpu_driven_tuning_run_equals_oracle_driven(ev3):
+    """the SAME batched tuning run (mpcgpu/tuner.py: goal attainment on the weights
+    alternating with VNS on the horizons, MPC_TFob.m:56-132) driven once by the GPU evaluator and once by the CPU oracle
+    behind the same eval_batch interface.  The search is deterministic (seeded), so as long as the costs agree to the
+    parity tolerance both runs visit the same candidates and end on the same tuning."""
+    from mpcgpu import tuner
+    p = ev3.prob
+    op = orc.OracleProblem(p)
+
+    class OracleEvaluator:
+        prob = p
+
+        def __init__(self):
+            self.n = 0
+
+        def eval_batch(self, N, Nu, delta, lam, mode="gam"):
+            N = np.ascontiguousarray(N, dtype=np.int32)
+            self.n += len(N)
+            cost, status, _ = orc.eval_batch(op, N, np.ascontiguousarray(Nu, dtype=np.int32), np.ascontiguousarray(delta, dtype=np.float64),
+                                             np.ascontiguousarray(lam, dtype=np.float64), mode)
+            cost = np.where((status != 0)[:, None] if cost.ndim == 2 else status != 0, np.nan, cost)
+            return {"cost": cost, "status": status}
+
+    kw = dict(w=[0.05, 0.40, 0.55], pop=96, iters=5, max_outer=2)      # w: Shell3x3.m:161
+    a = tuner.tune_linear(ev3, **kw)
+    oe = OracleEvaluator()
+    b = tuner.tune_linear(oe, **kw)
+    assert a["evaluations"] == b["evaluations"] == oe.n and a["evaluations"] > 1000
+    assert int(a["N"]) == int(b["N"]) and np.array_equal(a["Nu"], b["Nu"]), (a, b)
+    np.testing.assert_allclose(a["delta"], b["delta"], rtol=1e-6)
+    np.testing.assert_allclose(a["lam"], b["lam"], rtol=1e-6)
+    ga = ev3.eval_batch([a["N"]], [int(a["Nu"].max())], a["delta"][None], a["lam"][None], mode="gam")["cost"][0]
+    gb = oe.eval_batch([b["N"]], [int(b["Nu"].max())], b["delta"][None], b["lam"][None], mode="gam")["cost"][0]
+    np.testing.assert_allclose(ga, gb, rtol=1e-6)
