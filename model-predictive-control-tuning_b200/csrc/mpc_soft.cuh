@@ -33,9 +33,9 @@
 #define SOFT_WARM_START 0   /* 1: carry the active set across samples.  Measured (round 2, tools/soft_probe.py, gpurun_out/probe4.log, probe5.log):
                                2.6 x fewer iterations and 2.6 x less time (203 vs 541 ms for 256 full-range candidates), but 70 of 256
                                candidates that the oracle resolves to 1e-7 then differ by more than 1e-6, with or without a rebuild
-                               of the carried factor at every QP: the degenerate band rows (equal normals inside the dead time)
-                               make the multipliers of a carried set non-unique, and the shed / re-add sequence ends on another
-                               vertex of the same face within VIOL_TOL.  Off: parity first. */
+                               of the carried factor at every QP (so it is not factor drift; the cause is not established -- suspected:
+                               the degenerate band rows, equal normals inside the dead time, make the multipliers of a carried set
+                               non-unique).  Off: parity first. */
 #endif
 #ifndef SOFT_REFRESH_ROT
 #define SOFT_REFRESH_ROT 0   /* rotations after which J is rebuilt from H^-1 (cold-start mode).  0 = at every constrained QP: J drifts
