@@ -37,6 +37,16 @@
                                the degenerate band rows, equal normals inside the dead time, make the multipliers of a carried set
                                non-unique).  Off: parity first. */
 #endif
+#ifndef SOFT_PREFER_LAST
+#define SOFT_PREFER_LAST 1  /* cold start, but the constraints of the previous sample's final active set are tried first as pivots
+                               (any violated constraint is a valid Goldfarb-Idnani pivot: the optimum is the same, the path
+                               shorter, and such a pivot needs neither the predicted outputs of the whole horizon nor the
+                               arg-min over all 2 ny p + 4 nu m rows) */
+#endif
+#ifndef SOFT_POLISH
+#define SOFT_POLISH 1   /* at exit recompute the optimum from the final active set alone, z = z_unc + J1 R^-T (b_A - N_A' z_unc), instead of
+                           keeping the sum of the steps that led there: the result then depends on the set, not on the path */
+#endif
 #ifndef SOFT_REFRESH_ROT
 #define SOFT_REFRESH_ROT 0   /* rotations after which J is rebuilt from H^-1 (cold-start mode).  0 = at every constrained QP: J drifts
                                under the Givens rotations (cond(H) reaches 1e12 here), and a drifting J made the result depend on
@@ -60,51 +70,54 @@ static MPC_HD size_t soft_smem_doubles(const MpcLayout &L, int nu, int P) {
     n += (size_t)SIM_CH * (2 * L.ny + L.nd);  // sig
     n += R + 4 * nu + nu;                     // uopt, bnd, ucur
     n += (size_t)nch * HL + 2 * nch;          // xfh, base, dev
-    n += 6 * (size_t)NV;                      // z, lvl, w, wsc, dir, nrm
+    n += 7 * (size_t)NV;                      // z, lvl, w, wsc, dir, nrm, zu
     n += 4 * (size_t)QM;                      // g, l, rr, mu
     n += (size_t)QM * NV + (size_t)QM * QM;   // V, Li
     n += 2 * (size_t)nrow;                    // yfree, ypred
     n += SOFT_THREADS + 8;                    // reduction values, scalars
-    n += (3 * nch + L.nst + R + 2 * QM + SOFT_THREADS + 16 + (nrow + 3) / 4 + 1) / 2 + 2;   // ints
+    n += (3 * nch + L.nst + R + 3 * QM + SOFT_THREADS + 16 + (nrow + 3) / 4 + 1) / 2 + 2;   // ints
     return n;
 }
 
 struct SoftSm {
     double *st, *x, *xol, *hist, *cha, *chb0, *chb1, *chg, *sig, *uopt, *bnd, *ucur, *xfh, *base, *dev;
-    double *z, *lvl, *w, *wsc, *dir, *nrm, *g, *l, *rr, *mu, *V, *Li, *yfree, *ypred, *red, *sc;
-    int *chd, *chj, *cht0, *role, *amask, *act, *dflag, *redi, *misc;
+    double *z, *lvl, *w, *wsc, *dir, *nrm, *zu, *g, *l, *rr, *mu, *V, *Li, *yfree, *ypred, *red, *sc;
+    int *chd, *chj, *cht0, *role, *amask, *act, *dflag, *redi, *misc, *pref;
     unsigned char *ovmask;
 };
 
-// deterministic block reductions (fixed tree): every thread returns the result
+// deterministic block reductions (fixed order: shuffle tree inside each warp, then the warps' partial results in warp order):
+// every thread returns the result.  Two block barriers each; the first version (a seven-level tree through shared memory,
+// eight barriers) was a fifth of an active-set iteration.
+static_assert(SOFT_THREADS == 128, "four warps");
 __device__ __forceinline__ double soft_sum(double v, const SoftSm &sm) {
     const int tid = threadIdx.x;
-    sm.red[tid] = v;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((tid & 31) == 0) sm.red[tid >> 5] = v;
     SOFT_SYNC();
-    for (int s = SOFT_THREADS / 2; s > 0; s >>= 1) {
-        if (tid < s) sm.red[tid] += sm.red[tid + s];
-        SOFT_SYNC();
-    }
-    const double r = sm.red[0];
+    const double r = (sm.red[0] + sm.red[1]) + (sm.red[2] + sm.red[3]);
     SOFT_SYNC();
     return r;
 }
 // minimum value and, among equal values, the smallest non-negative index
 __device__ __forceinline__ void soft_argmin(double &v, int &i, const SoftSm &sm) {
     const int tid = threadIdx.x;
-    sm.red[tid] = v; sm.redi[tid] = i;
-    SOFT_SYNC();
-    for (int s = SOFT_THREADS / 2; s > 0; s >>= 1) {
-        if (tid < s) {
-            const double ov = sm.red[tid + s];
-            const int oi = sm.redi[tid + s];
-            if (ov < sm.red[tid] || (ov == sm.red[tid] && oi >= 0 && (sm.redi[tid] < 0 || oi < sm.redi[tid]))) {
-                sm.red[tid] = ov; sm.redi[tid] = oi;
-            }
-        }
-        SOFT_SYNC();
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, v, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, i, o);
+        if (ov < v || (ov == v && oi >= 0 && (i < 0 || oi < i))) { v = ov; i = oi; }
     }
+    if ((tid & 31) == 0) { sm.red[tid >> 5] = v; sm.redi[tid >> 5] = i; }
+    SOFT_SYNC();
     v = sm.red[0]; i = sm.redi[0];
+#pragma unroll
+    for (int w = 1; w < SOFT_THREADS / 32; ++w) {
+        const double ov = sm.red[w];
+        const int oi = sm.redi[w];
+        if (ov < v || (ov == v && oi >= 0 && (i < 0 || oi < i))) { v = ov; i = oi; }
+    }
     SOFT_SYNC();
 }
 
@@ -129,7 +142,7 @@ struct SoftQP {
     const MpcTables &T;
     SoftSm sm;
     const double *W;   // global: R x R inverse Hessian (padded layout)
-    int p, m, q, tid, n_rot, ne;
+    int p, m, q, tid, n_rot, ne, npref;
     unsigned long long n_con, n_it;
     int qmax;
 
@@ -493,11 +506,31 @@ struct SoftQP {
             for (int a = tid; a < q; a += SOFT_THREADS) if (sm.mu[a] < 0.0) sm.mu[a] = 0.0;
             SOFT_SYNC();
         }
+#if SOFT_POLISH
+        for (int r = tid; r < NV; r += SOFT_THREADS) sm.zu[r] = sm.z[r];
+        SOFT_SYNC();
+#endif
         // ---- Goldfarb-Idnani iterations ----
+        int pptr = 0;
         for (;;) {
-            evaluate(true);
             double bv = -SIM_VIOL_TOL;
             int bi = -1;
+#if SOFT_PREFER_LAST
+            if (pptr < npref) {   // next constraint of the previous sample's set that is violated and not active (uniform)
+                evaluate(false);
+                while (pptr < npref) {
+                    const int cid = sm.pref[pptr++];
+                    const int type = cid & 7, k = cid >> 3;
+                    const int isact = type < 4 ? (sm.amask[k] >> type) & 1 : (type == 6 ? sm.misc[4] : (sm.ovmask[k] >> (type == 4 ? 0 : 1)) & 1);
+                    if (isact) continue;
+                    const double sl = slack_of(cid);
+                    if (sl < -SIM_VIOL_TOL) { bi = cid; bv = sl; break; }
+                }
+                SOFT_SYNC();
+            }
+            if (bi < 0) {
+#endif
+            evaluate(true);
             auto take = [&](double s, int id) { if (s < bv || (s == bv && bi >= 0 && id < bi)) { bv = s; bi = id; } };
             for (int r = tid; r < R; r += SOFT_THREADS) {
                 const int j = r / P, c = r - j * P;
@@ -519,6 +552,9 @@ struct SoftQP {
             }
             if (tid == 0 && !sm.misc[4]) take(eps, 6);
             soft_argmin(bv, bi, sm);
+#if SOFT_PREFER_LAST
+            }
+#endif
             if (bi < 0) break;
             const int pv = bi;
             double sp = bv, mu_p = 0.0;
@@ -558,6 +594,18 @@ struct SoftQP {
                 self_check("drop");
             }
         }
+#if SOFT_POLISH
+        if (q > 0) {
+            for (int r = tid; r < NV; r += SOFT_THREADS) sm.z[r] = sm.zu[r];
+            SOFT_SYNC();
+            evaluate(false);
+            for (int a = tid; a < q; a += SOFT_THREADS) sm.g[a] = -slack_of(sm.act[a]);
+            SOFT_SYNC();
+            tri_lower();
+            add_J(0, q, sm.l, 1.0, sm.z);
+            evaluate(false);
+        }
+#endif
         // ---- one Newton correction on the active constraints: z += J1 R^-T (-slack_A) ----
         if (q > 0) {
             double worst = 0.0;
@@ -576,6 +624,12 @@ struct SoftQP {
         }
         n_it += it;
         if (q > qmax) qmax = q;
+#if SOFT_PREFER_LAST
+        SOFT_SYNC();
+        for (int a = tid; a < q; a += SOFT_THREADS) sm.pref[a] = sm.act[a];
+        npref = q;
+        SOFT_SYNC();
+#endif
         return 0;
     }
 };
@@ -605,7 +659,7 @@ __device__ __forceinline__ int soft_run(const MpcLayout &L, const MpcTables &T, 
         sm.sig = q_; q_ += (size_t)SIM_CH * nsig;
         sm.uopt = q_; q_ += R; sm.bnd = q_; q_ += 4 * NU; sm.ucur = q_; q_ += NU;
         sm.xfh = q_; q_ += (size_t)nch * HL; sm.base = q_; q_ += nch; sm.dev = q_; q_ += nch;
-        sm.z = q_; q_ += NV; sm.lvl = q_; q_ += NV; sm.w = q_; q_ += NV; sm.wsc = q_; q_ += NV; sm.dir = q_; q_ += NV; sm.nrm = q_; q_ += NV;
+        sm.z = q_; q_ += NV; sm.lvl = q_; q_ += NV; sm.w = q_; q_ += NV; sm.wsc = q_; q_ += NV; sm.dir = q_; q_ += NV; sm.nrm = q_; q_ += NV; sm.zu = q_; q_ += NV;
         sm.g = q_; q_ += QM; sm.l = q_; q_ += QM; sm.rr = q_; q_ += QM; sm.mu = q_; q_ += QM;
         sm.V = q_; q_ += (size_t)QM * NV; sm.Li = q_; q_ += (size_t)QM * QM;
         sm.yfree = q_; q_ += nrow; sm.ypred = q_; q_ += nrow;
@@ -613,10 +667,10 @@ __device__ __forceinline__ int soft_run(const MpcLayout &L, const MpcTables &T, 
         int *ip = (int *)q_;
         sm.chd = ip; ip += nch; sm.chj = ip; ip += nch; sm.cht0 = ip; ip += nch; sm.role = ip; ip += nst;
         sm.amask = ip; ip += R; sm.act = ip; ip += QM; sm.dflag = ip; ip += QM; sm.redi = ip; ip += SOFT_THREADS;
-        sm.misc = ip; ip += 16;
+        sm.misc = ip; ip += 16; sm.pref = ip; ip += QM;
         sm.ovmask = (unsigned char *)ip;
     }
-    qp.W = Wg; qp.p = p; qp.m = m; qp.q = 0; qp.tid = tid; qp.n_rot = 0; qp.n_con = 0; qp.n_it = 0; qp.qmax = 0;
+    qp.W = Wg; qp.p = p; qp.m = m; qp.q = 0; qp.tid = tid; qp.npref = 0; qp.n_rot = 0; qp.n_con = 0; qp.n_it = 0; qp.qmax = 0;
     qp.ne = NU * m + 1;
     // ---- one-time staging ----
     for (int ch = tid; ch < nch; ch += SOFT_THREADS) {
@@ -845,6 +899,7 @@ __device__ __forceinline__ int soft_run(const MpcLayout &L, const MpcTables &T, 
             }
             // the closed loop starts from an empty active set
             for (int a = qp.q - 1; a >= 0; --a) { qp.set_mask(sm.act[a], false); SOFT_SYNC(); }
+            qp.npref = 0;
             qp.q = 0;   // every column of J is complement basis again (J J' = H^-1 holds for any rotation of it)
             SOFT_SYNC();
             continue;

@@ -78,6 +78,7 @@ typedef struct {
 typedef struct {
     double *J, *R, *d, *z, *rv, *nv, *s, *u;
     int *A;
+    int *pref, npref;   /* final active set of the previous solve with this work area (pivot rule 2) */
 } gi_work;
 
 static gi_work *gi_alloc(int n, int mc) {
@@ -91,10 +92,12 @@ static gi_work *gi_alloc(int n, int mc) {
     w->s = (double *)malloc(sizeof(double) * (mc + 1));
     w->u = (double *)malloc(sizeof(double) * (n + 1));
     w->A = (int *)malloc(sizeof(int) * (n + 1));
+    w->pref = (int *)malloc(sizeof(int) * (n + 1));
+    w->npref = 0;
     return w;
 }
 static void gi_free(gi_work *w) {
-    free(w->J); free(w->R); free(w->d); free(w->z); free(w->rv); free(w->nv); free(w->s); free(w->u); free(w->A);
+    free(w->J); free(w->R); free(w->d); free(w->z); free(w->rv); free(w->nv); free(w->s); free(w->u); free(w->A); free(w->pref);
     free(w);
 }
 
@@ -130,8 +133,10 @@ static void gi_drop(gi_work *w, int n, int *q, int l) {
 
 /* x: in = unconstrained optimum -H^-1 f, out = constrained optimum.  J0 = L^-T (n x n, row-major).
  * Returns 0 ok, 1 infeasible, 2 iteration cap.  iters counts constraint additions + drops. */
-/* Pivot rule of the outer loop: 0 = most violated constraint (the default), 1 = first violated constraint in index order.
- * Both are valid Goldfarb-Idnani pivots and reach the same optimum in exact arithmetic; the spread between the two runs of
+/* Pivot rule of the outer loop: 0 = most violated constraint (the default), 1 = first violated constraint in index order,
+ * 2 = the violated constraints of the previous sample's final active set first, then the most violated (what the
+ * soft-constraint kernel does, SOFT_PREFER_LAST in csrc/mpc_soft.cuh).
+ * All are valid Goldfarb-Idnani pivots and reach the same optimum in exact arithmetic; the spread between the two runs of
  * the SAME oracle is the yard-stick tests/ and bench.py use for what fp64 can resolve on a candidate (oracle/parity.py). */
 static int g_pivot_rule = 0;
 void orc_set_pivot_rule(int rule) { g_pivot_rule = rule; }
@@ -148,6 +153,15 @@ static int gi_solve(const gi_constraints *cs, const double *J0, double *x, gi_wo
         cs->slacks(cs->ctx, x, s);
         int p = -1;
         double smin = -VIOL_TOL;
+        if (g_pivot_rule == 2) {
+            for (int e = 0; e < w->npref && p < 0; ++e) {
+                const int i = w->pref[e];
+                int act = 0;
+                for (int k = 0; k < q; ++k) if (A[k] == i) { act = 1; break; }
+                if (!act && s[i] < -VIOL_TOL) { smin = s[i]; p = i; }
+            }
+        }
+        if (p < 0)
         for (int i = 0; i < mc; ++i) {
             int act = 0;
             for (int k = 0; k < q; ++k) if (A[k] == i) { act = 1; break; }
@@ -219,6 +233,8 @@ static int gi_solve(const gi_constraints *cs, const double *J0, double *x, gi_wo
     }
     *iters = it;
     if (nact_out) *nact_out = q;
+    for (int k = 0; k < q; ++k) w->pref[k] = A[k];
+    w->npref = q;
     return 0;
 }
 

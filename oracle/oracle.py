@@ -97,7 +97,8 @@ def closedloop(op: OracleProblem, N: int, Nu: int, delta, lam, open_loop: bool =
 
 
 def set_pivot_rule(rule: int):
-    """0: most violated constraint first (default); 1: first violated in index order (resolution probe, oracle/parity.py)."""
+    """0: most violated constraint first (default); 1: first violated in index order; 2: the previous sample's final active set
+    first (resolution probes, oracle/parity.py)."""
     lib().orc_set_pivot_rule(int(rule))
 
 

@@ -129,9 +129,11 @@ static inline void simt_run_warp(const std::function<void()> &fn, unsigned block
     for (auto &t : th) t.join();
 }
 
-// run fn() as one CTA of `nthreads` threads (block-level code: __syncthreads only, no warp intrinsics)
+// run fn() as one CTA of `nthreads` threads (a multiple of 32): __syncthreads across the block, warp intrinsics inside each
+// group of 32 consecutive threads
 static inline void simt_run_block(const std::function<void()> &fn, unsigned nthreads) {
     std::barrier<> bar((std::ptrdiff_t)nthreads);
+    std::vector<SimtWarp> warps((nthreads + 31) / 32);
     std::vector<std::thread> th;
     for (unsigned l = 0; l < nthreads; ++l)
         th.emplace_back([&, l]() {
@@ -139,6 +141,7 @@ static inline void simt_run_block(const std::function<void()> &fn, unsigned nthr
             blockDim.x = nthreads;
             blockIdx.x = 0;
             simt_block = &bar;
+            simt_warp = &warps[l / 32];
             fn();
         });
     for (auto &t : th) t.join();
