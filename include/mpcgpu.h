@@ -129,6 +129,21 @@ int mpcgpu_cost_device_ptr(mpcgpu_handle *h, int cost_mode, void **ptr, int *cou
 enum { MPCGPU_OPT_VNS_LEGALITY = 1 };
 int mpcgpu_set_option(mpcgpu_handle *h, int option, int value);
 
+/* Plant-model mismatch validation run (/root/reference/MPC-Tuning/Shell3x3.m:271-286, WoodBerry.m:263-278, Shell7x5.m:293-306:
+ *   options = mpcsimopt(mpc_toolbox); options.Model = plant; [y,t,u] = sim(mpc_toolbox,nit,r,[],options)).
+ * After this call every evaluation of the handle (GAM cost or RAW trajectories y, u; ys / uopt are zero) simulates the
+ * controller against the REAL plant given here -- channels y(k) = a y(k-1) + b0 w(k-d) + b1 w(k-d-1), ny x nw row-major
+ * like mpcgpu_problem's, scaled like the model (L*Psr*R) -- while the controller keeps predicting with the handle's model
+ * and corrects its state at every sample with the estimator gain:
+ *   x_c(k|k) = x_c(k|k-1) + gain * (y(k) - C x_c(k|k-1)),   x_c = [channel states (ny*nw); MV delay-line states w_j(k-1-q),
+ *   q = 0..hl-1 (nu*hl); output-disturbance states (ny)],   gain: (ny*nw + nu*hl + ny) x ny row-major.
+ * The gain is an INPUT: the Toolbox's own `getEstimator(mpcobj)` mapped to this state order, or the restated Toolbox default
+ * (integrated white noise on every output, unit white noise on every MV and measurement, steady-state Kalman filter:
+ * mpcgpu/estimator.py default_estimator_gain).  plant_a == NULL: back to the nominal evaluation.  Runs on the general
+ * block-per-run kernel (hard MV limits and soft output limits alike); the VNS objective is not defined for it. */
+int mpcgpu_set_mismatch(mpcgpu_handle *h, const double *plant_a, const double *plant_b0, const double *plant_b1,
+                        const int32_t *plant_d, const double *gain, int hl);
+
 /* [y,u,t,ys,uopt] = closedloop_toolbox(mpc_toolbox,r,v,N,Nu,delta,lambda,nit) as ONE call
  * (/root/reference/MPC-Tuning/MPC_Tuning/closedloop_toolbox.m:1): r nit x ny, v nit x nd (NULL when nd == 0), N / Nu the
  * max of the caller's vectors (:38-40), outputs signals x time (ny|nu x nit, :103-107; any may be NULL), t = (0..nit-1)*Ts

@@ -21,6 +21,10 @@
  *                      either orientation (row2col.m), N / Nu vectors -> max (:38-40), outputs signals x time (:103-107);
  *                      the handle's own signals (Par.Xsp, Par.Yref) are untouched.  Needs P.Ts for t.
  *     mpcgpu_mex('option', h, 'vns_legality', 0|1)      VNS2.m:135 inside the library
+ *     mpcgpu_mex('mismatch', h, Pl, gain, hl)           validation run against a real plant that differs from the model
+ *                      (Shell3x3.m:271-286  options.Model = plant): Pl struct with a, b0, b1, d (ny x nw, row-major like P's),
+ *                      gain (ny*nw + nu*hl + ny) x ny MATLAB matrix of the state estimator (mpcgpu.h, mpcgpu_set_mismatch);
+ *                      mpcgpu_mex('mismatch', h) switches back to the nominal evaluation
  *     mpcgpu_mex('destroy', h) / mpcgpu_mex('destroy_multi', hm)
  *   nonlinear path (closedloop_toolbox_nmpc.m:1)
  *     hn = mpcgpu_mex('nmpc_create', Pn)                Pn: struct with the fields of mpcgpu_nmpc_problem
@@ -235,6 +239,22 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
         ARG(!mxGetString(prhs[2], name, sizeof(name)) && !strcmp(name, "vns_legality"), "unknown option");
         if (mpcgpu_set_option((mpcgpu_handle *)handle_of(prhs[1]), MPCGPU_OPT_VNS_LEGALITY, (int)mxGetScalar(prhs[3])) != MPCGPU_OK)
             mexErrMsgIdAndTxt("mpcgpu:arg", "set_option failed");
+    } else if (!strcmp(cmd, "mismatch")) {
+        ARG(nrhs == 2 || nrhs == 5, "mismatch: (h) or (h, plant struct, gain, hl)");
+        mpcgpu_handle *h = (mpcgpu_handle *)handle_of(prhs[1]);
+        if (nrhs == 2) {
+            if (mpcgpu_set_mismatch(h, NULL, NULL, NULL, NULL, NULL, 0) != MPCGPU_OK) mexErrMsgIdAndTxt("mpcgpu:arg", "%s", mpcgpu_last_error(h));
+        } else {
+            const int ix = lookup(h);
+            ARG(ix >= 0 && mxIsStruct(prhs[2]), "mismatch: unknown handle / plant struct expected");
+            const int hl = (int)mxGetScalar(prhs[4]);
+            const mwSize ns = (mwSize)(g_lin[ix].ny * (g_lin[ix].nu + g_lin[ix].nd) + g_lin[ix].nu * hl + g_lin[ix].ny);
+            double *gain = rows_of(prhs[3], ns, (mwSize)g_lin[ix].ny);
+            int32_t *d = i32_field(prhs[2], "d");
+            const int rc = mpcgpu_set_mismatch(h, f64(prhs[2], "a", 1), f64(prhs[2], "b0", 1), f64(prhs[2], "b1", 1), d, gain, hl);
+            mxFree(gain); mxFree(d);
+            if (rc != MPCGPU_OK) mexErrMsgIdAndTxt("mpcgpu:arg", "%s", mpcgpu_last_error(h));
+        }
     } else if (!strcmp(cmd, "destroy")) {
         void *h = handle_of(prhs[1]); forget(h); mpcgpu_destroy((mpcgpu_handle *)h);
     } else if (!strcmp(cmd, "destroy_multi")) {

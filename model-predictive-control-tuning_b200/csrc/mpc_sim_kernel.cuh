@@ -20,6 +20,7 @@ struct DevCand {
     long long scratch_stride;
     double *slot;     // per-run parking slots of the two-phase mode (sim_slot_doubles), or nullptr
     long long slot_stride;
+    const MpcEst *est;   // validation run against a mismatched plant (mpcgpu_set_mismatch), or nullptr
 };
 
 struct DevOut {
@@ -82,7 +83,7 @@ __global__ void __launch_bounds__(32, SPEC ? SIM_SPEC_MINB : 1) k_sim(const MpcL
 
 
 // One CTA per (candidate, run): plants with soft output constraints (mpc_soft.cuh).
-template <int NU, int P>
+template <int NU, int P, bool EST = false>
 __global__ void __launch_bounds__(SOFT_THREADS) k_soft(const MpcLayout L, const MpcTables T, const int *order, int count, int runs,
                                                        int mode, int square, long long item0, DevCand C, DevOut O) {
     extern __shared__ double smem_f[];
@@ -110,7 +111,8 @@ __global__ void __launch_bounds__(SOFT_THREADS) k_soft(const MpcLayout L, const 
     out.trace = nullptr;
     const long long t_start = clock64();
     const int sel = mode == 2 ? (square ? run : -1) : -2;
-    const int st = soft_run<NU, P>(L, T, C.N[c], C.Nu[c], C.M + C.offM[c], C.W + C.offW[c], mode, sel, smem_f, out);
+    const int st = soft_run<NU, P, EST>(L, T, C.N[c], C.Nu[c], C.M + C.offM[c], C.W + C.offW[c], mode, sel, smem_f, out,
+                                        EST ? C.est : nullptr, EST ? C.delta + (size_t)c * ny : nullptr);
     if (st != 0 && threadIdx.x == 0) atomicMax(O.status + c, st);
     if (out.diag && threadIdx.x == 0) out.diag[3] = (unsigned long long)(clock64() - t_start);
 }
@@ -136,3 +138,7 @@ sim_kernel_t soft_kernel_nu1(int P);
 sim_kernel_t soft_kernel_nu2(int P);
 sim_kernel_t soft_kernel_nu3(int P);
 sim_kernel_t soft_kernel_nu4(int P);
+sim_kernel_t soft_est_kernel_nu1();   // validation run against a mismatched plant: P = 16 image only
+sim_kernel_t soft_est_kernel_nu2();
+sim_kernel_t soft_est_kernel_nu3();
+sim_kernel_t soft_est_kernel_nu4();

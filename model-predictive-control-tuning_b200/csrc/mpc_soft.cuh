@@ -61,6 +61,19 @@ extern double *g_soft_dump;
 extern int g_soft_dump_k, g_soft_k;
 #endif
 
+// Plant-model mismatch validation run (Shell3x3.m:271-286: options.Model = plant): the real process and the controller's
+// state estimator (restated Toolbox default, mpcgpu/estimator.py E1-E4).  Device-resident, set by mpcgpu_set_mismatch.
+struct MpcEst {
+    double a[MPC_MAXY * MPC_MAXW], b0[MPC_MAXY * MPC_MAXW], b1[MPC_MAXY * MPC_MAXW];   // the real plant's channels
+    int d[MPC_MAXY * MPC_MAXW];
+    int hl;      // delay-line states per MV in the gain's state order
+    int hlp;     // length of the real plant's input histories (its longest delay + 2)
+    const double *gain;   // (ny*nw + nu*hl + ny) x ny, row-major: x_c(k|k) = x_c(k|k-1) + gain * (y - C x_c)
+};
+// extra shared memory of the validation kernel: xp, histp, xod, e, gvec, wy2
+static MPC_HD size_t soft_est_doubles(const MpcLayout &L, int nu, int P, int hlp) {
+    return (size_t)L.ny * L.nw + (size_t)L.nw * hlp + 3 * (size_t)L.ny + (size_t)nu * P + 2;
+}
 static MPC_HD size_t soft_smem_doubles(const MpcLayout &L, int nu, int P) {
     const int R = nu * P, NV = R + 1, QM = NV, nch = L.ny * L.nw, HL = sim_hl(L), nrow = L.ny * L.pmax;
     size_t n = 0;
@@ -637,9 +650,14 @@ struct SoftQP {
 // ------------------------------------------------------------------------------------------------
 // One closed-loop run by one CTA.  Arguments as sim_run (mpc_sim.cuh) plus the prediction horizon p.
 // ------------------------------------------------------------------------------------------------
-template <int NU, int P>
+// EST: the validation run against a real plant that differs from the model (MpcEst): the controller corrects its state
+// with the estimator gain at every sample and the unconstrained optimum is formed from the corrected free response,
+// z_unc = W G'Wy^2 (r - yfree), as the oracle does (the deviation-coordinate map M st has no column for a corrected
+// u(k-1) slot).  GAM / RAW only, no open-loop pass.
+template <int NU, int P, bool EST = false>
 __device__ __forceinline__ int soft_run(const MpcLayout &L, const MpcTables &T, int p, int m, const double *__restrict__ Mg,
-                                        const double *__restrict__ Wg, int mode, int sel, double *smem, const MpcRunOut &out) {
+                                        const double *__restrict__ Wg, int mode, int sel, double *smem, const MpcRunOut &out,
+                                        const MpcEst *E = nullptr, const double *delta = nullptr) {
     constexpr int R = NU * P;
     constexpr int NV = R + 1;
     constexpr int QM = NV;
@@ -669,6 +687,17 @@ __device__ __forceinline__ int soft_run(const MpcLayout &L, const MpcTables &T, 
         sm.amask = ip; ip += R; sm.act = ip; ip += QM; sm.dflag = ip; ip += QM; sm.redi = ip; ip += SOFT_THREADS;
         sm.misc = ip; ip += 16; sm.pref = ip; ip += QM;
         sm.ovmask = (unsigned char *)ip;
+    }
+    // validation run: the real plant's state and the estimator's extra state, behind the base layout
+    double *xp = nullptr, *histp = nullptr, *xod = nullptr, *einn = nullptr, *gvec = nullptr, *wy2 = nullptr;
+    int HLP = 0, headp = 0;
+    if (EST) {
+        HLP = E->hlp;
+        double *q_ = smem + soft_smem_doubles(L, NU, P);
+        xp = q_; q_ += nch; histp = q_; q_ += (size_t)nw * HLP; xod = q_; q_ += ny; einn = q_; q_ += ny; wy2 = q_; q_ += ny; gvec = q_;
+        for (int i = tid; i < nch; i += SOFT_THREADS) xp[i] = 0.0;
+        for (int i = tid; i < nw * HLP; i += SOFT_THREADS) histp[i] = 0.0;
+        for (int i = tid; i < ny; i += SOFT_THREADS) { xod[i] = 0.0; einn[i] = 0.0; const double w = delta[i] / L.sy[i]; wy2[i] = w * w; }
     }
     qp.W = Wg; qp.p = p; qp.m = m; qp.q = 0; qp.tid = tid; qp.npref = 0; qp.n_rot = 0; qp.n_con = 0; qp.n_it = 0; qp.qmax = 0;
     qp.ne = NU * m + 1;
@@ -708,7 +737,7 @@ __device__ __forceinline__ int soft_run(const MpcLayout &L, const MpcTables &T, 
         }
         return status;
     }
-    const bool want_ol = (mode != 1) || out.ys || out.uopt;
+    const bool want_ol = EST ? false : ((mode != 1) || out.ys || out.uopt);
     double jnu = 0.0;
     double cost_acc = 0.0;   // thread holding column stoff_e + i accumulates output i
 
@@ -732,7 +761,7 @@ __device__ __forceinline__ int soft_run(const MpcLayout &L, const MpcTables &T, 
                 const int i = a;
                 double yi = 0.0, ysi = 0.0, gsum = 0.0;
                 for (int j = 0; j < nw; ++j) {
-                    yi += sm.x[i * nw + j];
+                    yi += EST ? xp[i * nw + j] : sm.x[i * nw + j];   // validation run: the REAL plant's output is what is logged and costed
                     ysi += sm.xol[i * nw + j];
                     gsum += sm.chg[i * nw + j] * held(j, sigrow);
                 }
@@ -768,6 +797,7 @@ __device__ __forceinline__ int soft_run(const MpcLayout &L, const MpcTables &T, 
     };
     // z_unc = M st (M in global memory, [col][row]); slack row = 0.  Then the free response over the horizon.
     auto controller_move = [&](const double *sigrow) -> int {
+        if (!EST)
         for (int r = tid; r < NV; r += SOFT_THREADS) {
             double a0 = 0.0, a1 = 0.0;
             if (r < R) {
@@ -807,9 +837,32 @@ __device__ __forceinline__ int soft_run(const MpcLayout &L, const MpcTables &T, 
                 acc += (t <= t0) ? sm.xfh[ch * HL + t - 1]
                                  : fma(__ldg(T.PA + (size_t)ch * (L.pmax + 1) + (t - t0)), sm.dev[ch], sm.base[ch]);
             }
-            sm.yfree[row] = acc;
+            sm.yfree[row] = EST ? acc + xod[i] : acc;   // + the estimated output disturbance (an integrator: constant over the horizon)
         }
         SOFT_SYNC();
+        if (EST) {   // z_unc = W G'Wy^2 (r - yfree) from the corrected free response (oracle: ctx_move)
+            for (int r = tid; r < R; r += SOFT_THREADS) {
+                const int j = r / P, c = r - j * P;
+                double acc = 0.0;
+                if (c < m)
+                    for (int i = 0; i < ny; ++i) {
+                        const double *sp_ = T.ST + (size_t)(i * NU + j) * T.st_stride;
+                        const double w = wy2[i], ri = sigrow[i];
+                        double a = 0.0;
+                        for (int t = c + 1; t <= p; ++t) a = fma(__ldg(sp_ + (t - c)), ri - sm.yfree[(t - 1) * ny + i], a);
+                        acc = fma(w, a, acc);
+                    }
+                gvec[r] = acc;
+            }
+            SOFT_SYNC();
+            for (int r = tid; r < NV; r += SOFT_THREADS) {
+                double a0 = 0.0;
+                if (r < R)
+                    for (int r2 = 0; r2 < R; ++r2) a0 = fma(__ldg(Wg + (size_t)r * R + r2), gvec[r2], a0);
+                sm.z[r] = a0;
+            }
+            SOFT_SYNC();
+        }
         if (qp.q == 0) {   // fast exit: nothing carried and nothing violated
             qp.evaluate(true);
             int bad = 0;
@@ -868,6 +921,30 @@ __device__ __forceinline__ int soft_run(const MpcLayout &L, const MpcTables &T, 
             stage_signals(k);
         }
         const double *sigrow = ol ? sm.sig : sm.sig + (size_t)(k & (SIM_CH - 1)) * nsig;
+        if (EST) {   // measurement y(k) of the real plant, innovation, correction x_c(k|k) = x_c(k|k-1) + gain * e  (E4)
+            for (int i = tid; i < ny; i += SOFT_THREADS) {
+                double yp = 0.0, yh = xod[i];
+                for (int j = 0; j < nw; ++j) { yp += xp[i * nw + j]; yh += sm.x[i * nw + j]; }
+                einn[i] = yp - yh;
+            }
+            SOFT_SYNC();
+            const int hl = E->hl, hlm = hl < HL ? hl : HL;   // delay-line states beyond the model's longest delay never reach its outputs
+            const double *Gn = E->gain;
+            for (int s_ = tid; s_ < nch + NU * hlm + ny; s_ += SOFT_THREADS) {
+                int grow;
+                double *dst;
+                if (s_ < nch) { grow = s_; dst = sm.x + s_; }
+                else if (s_ < nch + NU * hlm) {
+                    const int j = (s_ - nch) / hlm, q_ = (s_ - nch) - j * hlm;
+                    int pos = head + q_; if (pos >= HL) pos -= HL;
+                    grow = nch + j * hl + q_; dst = sm.hist + j * HL + pos;
+                } else { const int o = s_ - nch - NU * hlm; grow = nch + NU * hl + o; dst = xod + o; }
+                double acc = *dst;
+                for (int i = 0; i < ny; ++i) acc = fma(__ldg(Gn + (size_t)grow * ny + i), einn[i], acc);
+                *dst = acc;
+            }
+            SOFT_SYNC();
+        }
         build_st(sigrow, ol ? nit - 1 : k, !ol);
         const unsigned long long it_before = qp.n_it;
 #ifdef MPC_SIMT_EMULATION
@@ -922,6 +999,14 @@ __device__ __forceinline__ int soft_run(const MpcLayout &L, const MpcTables &T, 
             const double w1 = dd == 0 ? wk : sm.hist[j * HL + p1];
             const double w0 = dd == 0 ? 0.0 : (dd == 1 ? wk : sm.hist[j * HL + p0]);
             sm.x[ch] = sm.cha[ch] * sm.x[ch] + sm.chb0[ch] * w0 + sm.chb1[ch] * w1;
+            if (EST) {   // the real plant, from the TRUE input history (slot q of histp holds w(k-1-q))
+                const int dp = E->d[ch];
+                int q1 = headp + (dp > 0 ? dp - 1 : 0); if (q1 >= HLP) q1 -= HLP;
+                int q0 = headp + (dp > 1 ? dp - 2 : 0); if (q0 >= HLP) q0 -= HLP;
+                const double v1 = dp == 0 ? wk : histp[j * HLP + q1];
+                const double v0 = dp == 0 ? 0.0 : (dp == 1 ? wk : histp[j * HLP + q0]);
+                xp[ch] = E->a[ch] * xp[ch] + E->b0[ch] * v0 + E->b1[ch] * v1;
+            }
             if (want_ol) {
                 double o1, o0;
                 if (j < NU) {
@@ -938,6 +1023,11 @@ __device__ __forceinline__ int soft_run(const MpcLayout &L, const MpcTables &T, 
         const int nhead = head == 0 ? HL - 1 : head - 1;
         if (tid < nw) sm.hist[tid * HL + nhead] = held(tid, sigrow);
         head = nhead;
+        if (EST) {
+            const int nhp = headp == 0 ? HLP - 1 : headp - 1;
+            if (tid < nw) histp[tid * HLP + nhp] = held(tid, sigrow);
+            headp = nhp;
+        }
         SOFT_SYNC();
     }
     // ---------------- costs ----------------

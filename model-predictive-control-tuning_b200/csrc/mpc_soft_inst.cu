@@ -1,7 +1,5 @@
-// mpc_soft_inst.cu -- instantiates k_soft<SIM_NU, P> (plants with soft output constraints) for P = 4, 8, 16.
-// Compiled with -fmad=false: the band-constraint QPs of Shell7x5 are degenerate enough that the pivot sequence of
-// the active-set method depends on the last bit of the slacks; without implicit multiply-add contraction the
-// kernel rounds like plain IEEE fp64 code (explicit fma() calls in the dot products stay fused).  DESIGN.md §2.
+// mpc_soft_inst.cu -- instantiates k_soft<SIM_NU, P> (plants with soft output constraints) for P = 4, 8, 16, and the
+// validation-run image k_soft<SIM_NU, 16, true> (mismatched plant + state estimator, any linear plant).
 #include "mpc_sim_kernel.cuh"
 
 #ifndef SIM_NU
@@ -18,3 +16,5 @@ sim_kernel_t SIM_CAT(soft_kernel_nu, SIM_NU)(int P) {
     }
     return nullptr;
 }
+
+sim_kernel_t SIM_CAT(soft_est_kernel_nu, SIM_NU)() { return k_soft<SIM_NU, 16, true>; }

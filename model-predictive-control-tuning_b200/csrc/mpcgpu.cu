@@ -60,6 +60,15 @@ static sim_kernel_t soft_kernel(int nu, int P) {
     }
     return nullptr;
 }
+static sim_kernel_t soft_est_kernel(int nu) {
+    switch (nu) {
+        case 1: return soft_est_kernel_nu1();
+        case 2: return soft_est_kernel_nu2();
+        case 3: return soft_est_kernel_nu3();
+        case 4: return soft_est_kernel_nu4();
+    }
+    return nullptr;
+}
 static sim_kernel_t sim_lean(int nu, int P) {
     switch (nu) {
         case 1: return sim_lean_nu1(P);
@@ -191,6 +200,10 @@ struct mpcgpu_handle {
     size_t smem_optin = 0;
     int sm_count = 148;
     int opt_vns_legality = 0;   // MPCGPU_OPT_VNS_LEGALITY
+    // validation run against a mismatched plant (mpcgpu_set_mismatch): device copy of MpcEst + the gain, or nullptr
+    MpcEst *dEst = nullptr;
+    double *dEstGain = nullptr;
+    int est_hlp = 0;
 };
 
 static MpcTables dev_tables(mpcgpu_handle *h) {
@@ -287,6 +300,8 @@ extern "C" int mpcgpu_create(const mpcgpu_problem *problem, int device, mpcgpu_h
     for (int v = 0; v < 3; ++v)
         if ((ce = cudaFuncSetAttribute(sim_spec(t.L.nu, v), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin)) != cudaSuccess)
             return fail("cudaFuncSetAttribute(k_sim spec)", ce);
+    if ((ce = cudaFuncSetAttribute(soft_est_kernel(t.L.nu), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin)) != cudaSuccess)
+        return fail("cudaFuncSetAttribute(k_soft est)", ce);
     // check the largest footprints fit
     const size_t sb = mpc_builder_smem_doubles(t.L.nu * t.L.mmax, t.L.nst) * sizeof(double);
     const size_t ss = (sim_spec_ok(t.L) ? sim_spec_smem_doubles(t.L, t.L.nu, 16) : sim_smem_doubles(t.L, t.L.nu, sim_pad(t.L.mmax))) * sizeof(double);
@@ -313,6 +328,8 @@ extern "C" void mpcgpu_destroy(mpcgpu_handle *h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->dEst) cudaFree(h->dEst);
+    if (h->dEstGain) cudaFree(h->dEstGain);
     h->dTG.release(); h->dTK.release(); h->dS1.release(); h->dST.release(); h->dPA.release(); h->dR.release(); h->dV.release(); h->dYref.release(); h->dSig.release();
     h->dN.release(); h->dNu.release(); h->dOrder.release(); h->dInvalid.release(); h->dBStatus.release();
     h->dStatus.release(); h->dStatus2.release(); h->dOffM.release(); h->dOffW.release(); h->dDelta.release(); h->dLambda.release();
@@ -470,7 +487,7 @@ extern "C" int mpcgpu_run(mpcgpu_handle *h, int cost_mode, int want_traj, void *
     if (scr_stride > 0 || two_phase) CK(h->dScratch.ensure((size_t)((scr_stride + (two_phase ? slot_stride : 0)) * scr_items + 1)));
     DevCand C{h->dN.p, h->dNu.p, h->dDelta.p, h->dLambda.p, h->dOffM.p, h->dOffW.p, h->dM.p, h->dW.p, h->dBStatus.p,
               scr_stride > 0 ? h->dScratch.p : nullptr, scr_stride,
-              two_phase ? h->dScratch.p + scr_stride * scr_items : nullptr, slot_stride};
+              two_phase ? h->dScratch.p + scr_stride * scr_items : nullptr, slot_stride, h->dEst};
     DevOut O{h->dCost.p, h->dPart.p, h->dStatus.p, h->dStatus2.p, h->dCounters.p,
              want_traj ? h->dY.p : nullptr, want_traj ? h->dU.p : nullptr, want_traj ? h->dYs.p : nullptr,
              want_traj ? h->dUopt.p : nullptr, nullptr};
@@ -517,7 +534,14 @@ extern "C" int mpcgpu_run(mpcgpu_handle *h, int cost_mode, int want_traj, void *
     for (int b = 0; b < nb; ++b) {
         const auto &bk = h->buckets[b];
         const int grid = bk.count * runs;
-        if (L.has_ov_bounds) {
+        if (h->dEst) {
+            // validation run: the block-per-run kernel with the estimator, whatever the plant's constraint set
+            if (bk.P != 16 || cost_mode == MPCGPU_COST_VNS) { h->err = "mismatch validation run: GAM / RAW only, single P = 16 bucket (unset MPCGPU_SIZE_BUCKETS)"; return MPCGPU_ERR_UNSUPPORTED; }
+            const size_t smem = (soft_smem_doubles(L, nu, 16) + soft_est_doubles(L, nu, 16, h->est_hlp)) * sizeof(double);
+            if (smem > h->smem_optin) { h->err = "mismatch validation run: shared memory"; return MPCGPU_ERR_UNSUPPORTED; }
+            soft_est_kernel(nu)<<<grid, SOFT_THREADS, smem, h->pool[b % NSTREAM]>>>(L, T, h->dOrder.p + bk.off, bk.count, runs,
+                                                                                cost_mode, square, item0, C, O);
+        } else if (L.has_ov_bounds) {
             const size_t smem = soft_smem_doubles(L, nu, bk.P) * sizeof(double);
             soft_kernel(nu, bk.P)<<<grid, SOFT_THREADS, smem, h->pool[b % NSTREAM]>>>(L, T, h->dOrder.p + bk.off, bk.count, runs,
                                                                                    cost_mode, square, item0, C, O);
@@ -648,6 +672,39 @@ extern "C" int mpcgpu_set_option(mpcgpu_handle *h, int option, int value) {
     }
     h->err = "unknown option";
     return MPCGPU_ERR_ARG;
+}
+
+// Plant-model mismatch validation (Shell3x3.m:271-286  options.Model = plant; sim(mpc, nit, r, [], options)): from this call on
+// every evaluation simulates the controller -- with its state estimator, gain given in the state order of mpcgpu/estimator.py
+// E1 -- against the real plant (a, b0, b1, d: ny x nw row-major like the model's).  plant_a == NULL switches it off again.
+extern "C" int mpcgpu_set_mismatch(mpcgpu_handle *h, const double *plant_a, const double *plant_b0, const double *plant_b1,
+                                   const int32_t *plant_d, const double *gain, int hl) {
+    if (!h) return MPCGPU_ERR_ARG;
+    CK(cudaSetDevice(h->device));
+    if (h->ran) CK(cudaEventSynchronize(h->ev_t2));
+    if (h->dEst) { cudaFree(h->dEst); h->dEst = nullptr; }
+    if (h->dEstGain) { cudaFree(h->dEstGain); h->dEstGain = nullptr; }
+    if (!plant_a) return MPCGPU_OK;
+    const MpcLayout &L = h->ht.L;
+    if (!plant_b0 || !plant_b1 || !plant_d || !gain || hl < 1) { h->err = "mpcgpu_set_mismatch: NULL argument / hl < 1"; return MPCGPU_ERR_ARG; }
+    const int nch = L.ny * L.nw;
+    MpcEst e;
+    memset(&e, 0, sizeof(e));
+    int dmax = 0;
+    for (int c = 0; c < nch; ++c) {
+        e.a[c] = plant_a[c]; e.b0[c] = plant_b0[c]; e.b1[c] = plant_b1[c]; e.d[c] = plant_d[c];
+        if (plant_d[c] < 0 || (plant_d[c] == 0 && plant_b0[c] != 0.0)) { h->err = "mpcgpu_set_mismatch: bad plant channel (d >= 0, b0 == 0 when d == 0)"; return MPCGPU_ERR_ARG; }
+        dmax = std::max(dmax, (int)plant_d[c]);
+    }
+    e.hl = hl; e.hlp = dmax + 2;
+    const size_t ng = (size_t)(nch + L.nu * hl + L.ny) * L.ny;
+    CK(cudaMalloc((void **)&h->dEstGain, sizeof(double) * ng));
+    CK(cudaMemcpy(h->dEstGain, gain, sizeof(double) * ng, cudaMemcpyHostToDevice));
+    e.gain = h->dEstGain;
+    CK(cudaMalloc((void **)&h->dEst, sizeof(MpcEst)));
+    CK(cudaMemcpy(h->dEst, &e, sizeof(MpcEst), cudaMemcpyHostToDevice));
+    h->est_hlp = e.hlp;
+    return MPCGPU_OK;
 }
 
 // closedloop_toolbox.m:1 as ONE call: the signals of the call are installed for this evaluation only and the handle's

@@ -87,6 +87,7 @@ def load_library():
     lib.mpcgpu_get_counters.argtypes = [C.c_void_p, C.POINTER(Counters)]
     lib.mpcgpu_measure_fp64_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
     lib.mpcgpu_set_option.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    lib.mpcgpu_set_mismatch.argtypes = [C.c_void_p] + [C.c_void_p] * 5 + [C.c_int]
     lib.mpcgpu_closedloop.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32] + [C.c_void_p] * 7
     lib.mpcgpu_create_multi.argtypes = [C.POINTER(ProblemStruct), C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
     lib.mpcgpu_destroy_multi.argtypes = [C.c_void_p]
@@ -121,7 +122,7 @@ def load_library():
 EXPORTED_SYMBOLS = [
     "mpcgpu_create", "mpcgpu_destroy", "mpcgpu_set_signals", "mpcgpu_eval_batch", "mpcgpu_upload", "mpcgpu_run",
     "mpcgpu_download", "mpcgpu_cost_device_ptr", "mpcgpu_get_counters", "mpcgpu_last_error", "mpcgpu_device_count",
-    "mpcgpu_measure_fp64_peak", "mpcgpu_set_option", "mpcgpu_closedloop",
+    "mpcgpu_measure_fp64_peak", "mpcgpu_set_option", "mpcgpu_closedloop", "mpcgpu_set_mismatch",
     "mpcgpu_create_multi", "mpcgpu_destroy_multi", "mpcgpu_multi_device_count", "mpcgpu_multi_set_option",
     "mpcgpu_multi_set_signals", "mpcgpu_multi_eval_batch", "mpcgpu_multi_get_counters", "mpcgpu_multi_last_error",
     "mpcgpu_work_estimate",

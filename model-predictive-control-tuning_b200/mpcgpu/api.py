@@ -156,6 +156,22 @@ class Evaluator:
         """e.g. set_option(OPT_VNS_LEGALITY, 1): VNS2.m:135 legality (N <= dmin, Nu <= 1 -> status 4) inside the library."""
         self._check(self.lib.mpcgpu_set_option(self.h, int(option), int(value)), "mpcgpu_set_option")
 
+    def set_mismatch(self, plant=None, gain=None, hl=None):
+        """Validation run against a real plant that differs from the model (Shell3x3.m:271-286): `plant` a Channels object
+        scaled like the model (mpcgpu.estimator.*_real_plant), `gain` the estimator gain in the state order of
+        mpcgpu/estimator.py E1 (default: the restated Toolbox default, default_estimator_gain).  plant=None: nominal again."""
+        if plant is None:
+            self._check(self.lib.mpcgpu_set_mismatch(self.h, None, None, None, None, None, 0), "mpcgpu_set_mismatch")
+            return
+        from . import estimator
+        hl = estimator.history_length(self.prob, plant) if hl is None else int(hl)
+        gain = estimator.default_estimator_gain(self.prob, hl) if gain is None else gain
+        keep = [np.ascontiguousarray(x, dtype=np.float64) for x in (plant.a, plant.b0, plant.b1)]
+        d = np.ascontiguousarray(plant.d, dtype=np.int32)
+        g = np.ascontiguousarray(gain, dtype=np.float64)
+        assert g.shape == (self.ny * (self.nu + self.nd) + self.nu * hl + self.ny, self.ny), g.shape
+        self._check(self.lib.mpcgpu_set_mismatch(self.h, _ptr(keep[0]), _ptr(keep[1]), _ptr(keep[2]), _ptr(d), _ptr(g), hl), "mpcgpu_set_mismatch")
+
     def closedloop(self, r, v, N, Nu, delta, lam, nit):
         """mpcgpu_closedloop: one closedloop_toolbox call with per-call signals; the handle's own signals are untouched."""
         nit = int(nit)

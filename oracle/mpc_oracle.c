@@ -252,6 +252,7 @@ typedef struct {
     double *H, *Lc, *J0; /* nz x nz */
     double *yfree; /* ny*p */
     const double *uprev; /* nu, set per step */
+    const double *yoff;  /* ny or NULL: estimated output disturbance, constant over the horizon (orc_closedloop_est) */
     double *f, *x;
 } cand_ctx;
 
@@ -418,6 +419,9 @@ static int ctx_move(cand_ctx *c, gi_work *gw, const double *xs, const double *wh
                 c->yfree[(t - 1) * ny + i] += xf;
             }
         }
+    if (c->yoff)
+        for (int t = 0; t < p; ++t)
+            for (int i = 0; i < ny; ++i) c->yfree[t * ny + i] += c->yoff[i];
     /* f = -G' Wy^2 (r - yfree) */
     for (int e = 0; e < nz; ++e) c->f[e] = 0.0;
     for (int t = 0; t < p; ++t)
@@ -540,6 +544,91 @@ int orc_closedloop(const orc_problem *pb, int p, int m, const double *delta, con
     }
     if (stats) { stats[0] += nqp; stats[1] += nit_as; stats[2] += nqp_act; }
     free(xs); free(wh); free(hv); free(up); free(wk);
+    gi_free(gw);
+    ctx_free(&c);
+    return status;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* Plant-model mismatch validation run (Shell3x3.m:271-286, WoodBerry.m:263-278, Shell7x5.m:293-306):   */
+/*   options = mpcsimopt(mpc); options.Model = plant; sim(mpc, nit, r, [], options)                     */
+/* The controller no longer sees the plant's state: it runs the Toolbox's state estimator.  Restated    */
+/* (PARITY UNPINNED, "Controller State Estimation" in the Toolbox documentation):                       */
+/*   E1  controller state x_c = [model channel states; MV delay-line states; output-disturbance states] */
+/*   E2  default output-disturbance model: one discrete integrator per measured output, driven by       */
+/*       unit-variance white noise; default measurement-noise model: unit-variance white noise          */
+/*   E3  unit-variance white noise added to every MV (the Toolbox's robustness term); MDs are known     */
+/*   E4  steady-state Kalman filter of that model; per sample                                           */
+/*         x_c(k|k) = x_c(k|k-1) + M (y(k) - C x_c(k|k-1)),  mpcmove from x_c(k|k),                      */
+/*         x_c(k+1|k) = A x_c(k|k) + B u(k)                                                             */
+/* The gain M is an INPUT here, (nch + nu*hl + ny) x ny row-major in the state order of E1 (delay-line  */
+/* state q of input j = w_j(k-1-q)); tests compute it from E2-E3 with scipy's DARE (tests/, mpcgpu.estimator). */
+/* plant: the real process, same channel structure as the model (pa, pb0, pb1, pd).                     */
+/* ------------------------------------------------------------------------------------------ */
+int orc_closedloop_est(const orc_problem *pb, const double *pa, const double *pb0, const double *pb1, const int *pd,
+                       const double *M, int p, int m, const double *delta, const double *lambda, double *y, double *u,
+                       long long *stats) {
+    const int ny = pb->ny, nu = pb->nu, nd = pb->nd, nw = nu + nd, nit = pb->nit, nch = ny * nw;
+    cand_ctx c;
+    memset(&c, 0, sizeof(c));
+    int rc = ctx_build(&c, pb, p, m, delta, lambda);
+    if (rc) { ctx_free(&c); return rc; }
+    gi_work *gw = gi_alloc(c.nz, 4 * c.nzu + 2 * ny * p + 1);
+    int dmax = 0;
+    for (int i = 0; i < nch; ++i) { if (pb->d[i] > dmax) dmax = pb->d[i]; if (pd[i] > dmax) dmax = pd[i]; }
+    const int hl = dmax + 2;
+    double *xs = (double *)calloc(nch, sizeof(double));              /* controller: model channel states */
+    double *wh = (double *)calloc((size_t)nw * hl, sizeof(double));  /* controller: input histories (MV rows estimated) */
+    double *xod = (double *)calloc(ny, sizeof(double));              /* controller: output-disturbance states */
+    double *xp = (double *)calloc(nch, sizeof(double));              /* plant channel states */
+    double *whp = (double *)calloc((size_t)nw * hl, sizeof(double)); /* plant: true input histories */
+    double *hv = (double *)calloc(nw, sizeof(double));
+    double *up = (double *)calloc(nu, sizeof(double));
+    double *wk = (double *)calloc(nw, sizeof(double));
+    double *e = (double *)calloc(ny, sizeof(double));
+    long long nqp = 0, nit_as = 0, nqp_act = 0;
+    int status = 0;
+    c.yoff = xod;
+    for (int k = 0; k < nit; ++k) {
+        /* measurement and correction (E4) */
+        for (int i = 0; i < ny; ++i) {
+            double yp = 0.0, yh = xod[i];
+            for (int j = 0; j < nw; ++j) { yp += xp[i * nw + j]; yh += xs[i * nw + j]; }
+            y[i * nit + k] = yp;
+            e[i] = yp - yh;
+        }
+        for (int s = 0; s < nch; ++s)
+            for (int i = 0; i < ny; ++i) xs[s] += M[(size_t)s * ny + i] * e[i];
+        for (int j = 0; j < nu; ++j)
+            for (int q = 0; q < hl; ++q)
+                for (int i = 0; i < ny; ++i) wh[j * hl + q] += M[(size_t)(nch + j * hl + q) * ny + i] * e[i];
+        for (int o = 0; o < ny; ++o)
+            for (int i = 0; i < ny; ++i) xod[o] += M[(size_t)(nch + nu * hl + o) * ny + i] * e[i];
+        /* controller move from the corrected state */
+        for (int j = 0; j < nu; ++j) hv[j] = up[j];
+        for (int j = 0; j < nd; ++j) hv[nu + j] = pb->v[k * nd + j];
+        int iters = 0, nact = 0;
+        rc = ctx_move(&c, gw, xs, wh, hl, hv, pb->r + (size_t)k * ny, up, &iters, &nact);
+        if (rc) status = rc;
+        nqp++; nit_as += iters; if (nact > 0) nqp_act++;
+        for (int j = 0; j < nu; ++j) { up[j] += c.x[j]; u[j * nit + k] = up[j]; wk[j] = up[j]; }
+        for (int j = 0; j < nd; ++j) wk[nu + j] = pb->v[k * nd + j];
+        /* time update of the controller state (model) and step of the real plant, both with the true w(k) */
+        for (int j = 0; j < nw; ++j) {
+            for (int qh = hl - 1; qh > 0; --qh) { wh[j * hl + qh] = wh[j * hl + qh - 1]; whp[j * hl + qh] = whp[j * hl + qh - 1]; }
+            wh[j * hl] = wk[j]; whp[j * hl] = wk[j];
+        }
+        for (int i = 0; i < ny; ++i)
+            for (int j = 0; j < nw; ++j) {
+                const int ch = i * nw + j;
+                int dd = pb->d[ch];
+                xs[ch] = pb->a[ch] * xs[ch] + pb->b0[ch] * (dd >= 1 ? wh[j * hl + dd - 1] : 0.0) + pb->b1[ch] * wh[j * hl + dd];
+                dd = pd[ch];
+                xp[ch] = pa[ch] * xp[ch] + pb0[ch] * (dd >= 1 ? whp[j * hl + dd - 1] : 0.0) + pb1[ch] * whp[j * hl + dd];
+            }
+    }
+    if (stats) { stats[0] += nqp; stats[1] += nit_as; stats[2] += nqp_act; }
+    free(xs); free(wh); free(xod); free(xp); free(whp); free(hv); free(up); free(wk); free(e);
     gi_free(gw);
     ctx_free(&c);
     return status;

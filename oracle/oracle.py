@@ -96,6 +96,19 @@ def closedloop(op: OracleProblem, N: int, Nu: int, delta, lam, open_loop: bool =
     return y, u, ys, uo, rc, stats
 
 
+def closedloop_est(op: OracleProblem, plant, M, N: int, Nu: int, delta, lam):
+    """Mismatch validation run (orc_closedloop_est): `plant` = the real process (Channels, scaled like the model), M = the
+    estimator gain in the state order of mpc_oracle.c E1.  Returns y, u (signals x time), status, stats."""
+    ny, nu, nit = op.ny, op.nu, op.nit
+    y = np.zeros((ny, nit)); u = np.zeros((nu, nit))
+    stats = np.zeros(3, dtype=np.int64)
+    keep = [_f64(plant.a), _f64(plant.b0), _f64(plant.b1), np.ascontiguousarray(plant.d, dtype=np.int32), _f64(M), _f64(delta), _f64(lam)]
+    P = lambda a: a.ctypes.data_as(C.c_void_p)
+    rc = lib().orc_closedloop_est(C.byref(op.c), P(keep[0]), P(keep[1]), P(keep[2]), P(keep[3]), P(keep[4]), int(N), int(Nu),
+                                  P(keep[5]), P(keep[6]), P(y), P(u), P(stats))
+    return y, u, rc, stats
+
+
 def set_pivot_rule(rule: int):
     """0: most violated constraint first (default); 1: first violated in index order; 2: the previous sample's final active set
     first (resolution probes, oracle/parity.py)."""

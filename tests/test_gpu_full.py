@@ -168,3 +168,48 @@ def test_gpu_driven_tuning_run_equals_oracle_driven(ev3):
     ga = ev3.eval_batch([a["N"]], [int(a["Nu"].max())], a["delta"][None], a["lam"][None], mode="gam")["cost"][0]
     gb = oe.eval_batch([b["N"]], [int(b["Nu"].max())], b["delta"][None], b["lam"][None], mode="gam")["cost"][0]
     np.testing.assert_allclose(ga, gb, rtol=1e-6)
+
+
+@pytest.mark.parametrize("case", ["shell3x3", "woodberry", "shell7x5"])
+def test_mismatch_validation_run(case):
+    """the validation run of the case scripts (Shell3x3.m:271-286, WoodBerry.m:263-278, Shell7x5.m:293-306:
+    options.Model = plant) -- the tuned controller against a plant with gain (and, Wood-Berry, dead-time) errors, the
+    controller running its state estimator (restated Toolbox default, mpcgpu/estimator.py).  GPU vs oracle on the trajectories
+    and the GAM cost; with the nominal plant the run must reproduce the ordinary closed loop (zero innovation)."""
+    from mpcgpu import estimator as est
+    p = {"shell3x3": lambda: mpcgpu.shell3x3(2), "woodberry": mpcgpu.woodberry, "shell7x5": mpcgpu.shell7x5}[case]()
+    plant = {"shell3x3": est.shell3x3_real_plant, "woodberry": est.woodberry_real_plant, "shell7x5": est.shell7x5_real_plant}[case]()
+    ev = mpcgpu.Evaluator(p, device=0)
+    op = orc.OracleProblem(p)
+    hl = est.history_length(p, plant)
+    M = est.default_estimator_gain(p, hl)
+    if case == "shell7x5":    # the reference's own tuned result (Shell7x5_Tuning_*.mat: N, Nu, lambda; delta = 0, band control)
+        cands = [(19, 7, np.zeros(7), np.array([0.056, 0.0167, 1.61])), (30, 4, np.zeros(7), np.array([0.5, 0.5, 0.5]))]
+    else:
+        cands = [(12, 4, np.full(p.ny, 0.5), np.full(p.nu, 0.3)), (30, 6, np.full(p.ny, 1.0), np.full(p.nu, 0.1)), (20, 2, np.full(p.ny, 0.2), np.full(p.nu, 1.0))]
+    N = np.array([c[0] for c in cands], dtype=np.int32); Nu = np.array([c[1] for c in cands], dtype=np.int32)
+    dl = np.array([c[2] for c in cands]); lm = np.array([c[3] for c in cands])
+    nominal = ev.eval_batch(N, Nu, dl, lm, mode="gam", traj=True)
+    # (1) estimator on, plant == model: zero innovation, the ordinary closed loop
+    ev.set_mismatch(p.plant, M, hl)
+    same = ev.eval_batch(N, Nu, dl, lm, mode="gam", traj=True)
+    assert (same["status"] == 0).all()
+    assert np.abs(same["y"] - nominal["y"]).max() < 1e-9 and np.abs(same["u"] - nominal["u"]).max() < 1e-9
+    # (2) the real plant
+    ev.set_mismatch(plant, M, hl)
+    out = ev.eval_batch(N, Nu, dl, lm, mode="gam", traj=True)
+    assert (out["status"] == 0).all()
+    for c in range(len(N)):
+        y, u, rc, _ = orc.closedloop_est(op, plant, M, int(N[c]), int(Nu[c]), dl[c], lm[c])
+        assert rc == 0
+        assert np.abs(out["y"][c] - y).max() < 1e-5 and np.abs(out["u"][c] - u).max() < 1e-5, (case, c, np.abs(out["y"][c] - y).max(), np.abs(out["u"][c] - u).max())
+        g = ((y - op.yref) ** 2).sum(axis=1)
+        np.testing.assert_allclose(out["cost"][c], g, rtol=1e-6, atol=1e-12)
+        assert np.abs(y - nominal["y"][c]).max() > 1e-4          # the mismatch is visible ...
+    if case != "shell7x5":
+        assert np.abs(out["y"][0, :, -1] - p.r[-1]).max() < 5e-3   # ... and the output-disturbance integrators remove the offset (first, fastest tuning)
+    # (3) off again
+    ev.set_mismatch(None)
+    back = ev.eval_batch(N, Nu, dl, lm, mode="gam", traj=True)
+    assert np.array_equal(back["y"], nominal["y"]) and np.array_equal(back["cost"], nominal["cost"])
+    ev.close()
