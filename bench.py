@@ -27,8 +27,22 @@ for _p in (ROOT, PKG):
 
 import numpy as np  # noqa: E402
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of the closed-loop kernel, from profiles/ (mode, population per GPU)
-TRAFFIC_NCU = {("gam", 4096): 64.6e6}
+def ncu_traffic(summary_file, kernel_substr, grid):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of a kernel, read from the committed `ncu --set full` summary
+    under profiles/ (profiles/summarize.py) -- only if that capture had the same grid (same population); else None."""
+    try:
+        for o in json.load(open(os.path.join(ROOT, "profiles", summary_file))):
+            if kernel_substr in o.get("Kernel Name", "") and o.get("Grid Size", "").startswith("(%d," % grid):
+                tot = 0.0
+                for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                    v, u = o[k].split()[:2]
+                    tot += float(v) * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
+                return tot
+    except Exception:
+        pass
+    return None
+
+
 METRIC = "closed-loop tuning candidates/sec (Shell3x3)"
 UNIT = "candidates/s"
 
@@ -362,7 +376,9 @@ def run_other(args):
                 "roofline": {"bound": "fp64_fma (serial per-run chains; neither hbm nor tensor)", "achieved": achieved, "peak": fp64_peak,
                              "unit": "TFLOP/s", "frac": achieved / fp64_peak if fp64_peak else None,
                              "kernel": "k_dtc (warp per candidate)" if args.config == "dtc" else "k_nmpc_g<16> (sixteen lanes per run, two runs per warp, sorted by horizons)",
-                             "algorithmic_flops_per_launch": fl, "traffic": None,
+                             "algorithmic_flops_per_launch": fl,
+                             "traffic": None if args.config == "dtc" else ncu_traffic("r2_other_kernels.json", "k_nmpc_g", (n + 1) // 2),
+                             "traffic_source": "profiles/r2_other_kernels.json (ncu --set full, same population; null otherwise)",
                              "peak_source": "mpcgpu_measure_fp64_peak, measured live"},
                 "failed_candidates": int((~ok).sum())}
         if not args.no_cpu_baseline and world == 1:
@@ -383,7 +399,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--pop", type=int, default=0, help="candidates per GPU (default: 4096; shell7x5 2048; dtc 16384; vdv 2048)")
+    ap.add_argument("--pop", type=int, default=0, help="candidates per GPU (default: 4096; shell7x5 2048; dtc 16384; vdv 16384)")
     ap.add_argument("--mode", default="gam", choices=["gam", "vns"])
     ap.add_argument("--no-other-configs", action="store_true", help="skip the Shell7x5 / DTC-GPC / NMPC context numbers")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -396,7 +412,7 @@ def main():
     ap.add_argument("--lam", default="", help="lo,hi : override the lambda range only (diagnostics)")
     args = ap.parse_args()
     if args.pop <= 0:
-        args.pop = {"shell3x3": 4096, "shell7x5": 2048, "dtc": 16384, "vdv": 2048}[args.config]
+        args.pop = {"shell3x3": 4096, "shell7x5": 2048, "dtc": 16384, "vdv": 16384}[args.config]
     if args.config in ("dtc", "vdv"):
         return run_other(args)
     if args.impl == "reference":
@@ -583,7 +599,9 @@ def main():
                                  "peak_gbs": peaks.get("hbm_gbs"), "frac": (hbm_alg / (sim_ms + build_ms) / 1e6) / peaks["hbm_gbs"] if peaks.get("hbm_gbs") else None},
                          # dram__bytes_read.sum + dram__bytes_write.sum of the closed-loop kernel of one population: not
                          # measurable inside bench.py (needs ncu); cited from the committed capture of the same command
-                         "traffic": TRAFFIC_NCU.get((args.mode, n)), "traffic_source": "profiles/r2_k_sim_summary.json (ncu --set full, same population)"},
+                         "traffic": (ncu_traffic("r2_other_kernels.json", "k_soft", n * runs) if (np.isfinite(prob.ymin).any() or np.isfinite(prob.ymax).any())
+                                     else ncu_traffic("r2_k_sim_summary.json", "k_sim", n * runs)) if args.mode == "gam" else None,
+                         "traffic_source": "profiles/r2_k_sim_summary.json / r2_other_kernels.json (ncu --set full of the same kernel on the same population; null if the population differs)"},
             "counters": {k: cn[k] for k in ("qp_constrained", "as_iterations", "qp_solves", "closed_loops")},
             "failed_candidates": nfail,
         }

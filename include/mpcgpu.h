@@ -43,7 +43,10 @@ enum {
     MPCGPU_CAND_NOT_PD = 3,       /* Hessian not positive definite (lambda == 0 and rank-deficient G) */
     MPCGPU_CAND_INVALID = 4,      /* horizons illegal: p < 2, m < 1, m >= p, beyond pmax / mmax; with MPCGPU_OPT_VNS_LEGALITY also
                                      VNS2.m:135 (N <= dmin_i for some output, Nu <= 1) -- PreCon.m:23 is m >= p            */
-    MPCGPU_CAND_BOUND_CROSSED = 5 /* NMPC only: a state/OV bound (soft in the Toolbox, not enforced here) was crossed; cost is still returned */
+    MPCGPU_CAND_BOUND_CROSSED = 5 /* NMPC only: the closed loop crossed an OV bound (soft in nlmpc, Weights.ECR) or a state bound (hard in
+                                     nlmpc) of VanDeVusse_NMPC.m:140-145.  The restated NLP does NOT enforce them (they are inactive in the
+                                     reference's tuning scenario); the cost of the unconstrained trajectory is returned and flagged, and
+                                     the host wrappers reject such a candidate by default (cost = inf) */
 };
 
 /* cost modes */

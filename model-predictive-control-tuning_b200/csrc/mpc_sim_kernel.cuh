@@ -83,8 +83,11 @@ __global__ void __launch_bounds__(32, SPEC ? SIM_SPEC_MINB : 1) k_sim(const MpcL
 
 
 // One CTA per (candidate, run): plants with soft output constraints (mpc_soft.cuh).
+#ifndef SOFT_MINB
+#define SOFT_MINB 3   /* resident CTAs per SM the register budget is sized for (no spills; 575 -> 550 ms on 2048 Shell7x5 candidates) */
+#endif
 template <int NU, int P, bool EST = false>
-__global__ void __launch_bounds__(SOFT_THREADS) k_soft(const MpcLayout L, const MpcTables T, const int *order, int count, int runs,
+__global__ void __launch_bounds__(SOFT_THREADS, SOFT_MINB) k_soft(const MpcLayout L, const MpcTables T, const int *order, int count, int runs,
                                                        int mode, int square, long long item0, DevCand C, DevOut O) {
     extern __shared__ double smem_f[];
     const int item = blockIdx.x;

@@ -132,6 +132,8 @@ class NmpcEvaluator:
         except Exception:
             pass
 
+    reject_bound_crossing = True   # eval_batch: cost = inf for candidates whose closed loop crossed an OV / state bound (status 5)
+
     def counters(self) -> dict:
         from . import _capi
         c = _capi.Counters()
@@ -157,6 +159,11 @@ class NmpcEvaluator:
                                              ptr(tr[0]), ptr(tr[1]), ptr(tr[2]), ptr(tr[3]), ptr(status))
         if rc != 0:
             raise self._err(f"mpcgpu_nmpc_eval_batch failed ({rc}): {self.lib.mpcgpu_nmpc_last_error(self.h).decode()}")
+        if cost is not None and self.reject_bound_crossing:
+            # status 5: the closed loop crossed an OV / state bound of VanDeVusse_NMPC.m:140-145, which nlmpc would have kept
+            # (OV bounds soft with Weights.ECR, state bounds hard) and this solver does not enforce -- such a candidate must not
+            # compete with costs from trajectories the Toolbox would have constrained: rejected (inf), like an illegal one
+            cost[status == 5] = np.inf
         out = {"cost": cost, "status": status}
         if tr[0] is not None:
             out.update(y=tr[0], u=tr[1], yopt=tr[2], uopt=tr[3])
