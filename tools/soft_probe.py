@@ -17,7 +17,8 @@ rel = (np.abs(out["cost"] - g0) / np.maximum(np.abs(g0), 1e-300)).max(axis=1)
 print(os.environ.get("MPCGPU_LIB", "default"), "kernel ms %.0f" % c["last_sim_ms"], "iterations", c["as_iterations"], "status", np.bincount(out["status"]).tolist(), np.bincount(st0).tolist())
 print("  rel<=1e-6: %d of %d; out of tol (max(1e-6,10 sens)): %d; well-posed (sens<1e-7) and rel>1e-6: %d" % ((rel <= 1e-6).sum(), n, (rel > np.maximum(1e-6, 10 * sens)).sum(), ((sens < 1e-7) & (rel > 1e-6)).sum()))
 bad = np.where(rel > 1e-6)[0]
-for cidx in bad[:40]:
+bad = bad[np.argsort(-(rel[bad] / np.maximum(1e-6, 10 * sens[bad])))]   # worst offenders (relative to their tolerance) first
+for cidx in bad[:int(os.environ.get('PROBE_LIST', 40))]:
     y, u, ys, uo, rc, stt = orc.closedloop(op, int(N[cidx]), int(Nu[cidx]), dl[cidx], lm[cidx])
     du = np.abs(out["u"][cidx] - u).max(axis=0); dy = np.abs(out["y"][cidx] - y).max(axis=0)
     k1 = np.argmax(du > 1e-9) if (du > 1e-9).any() else -1
