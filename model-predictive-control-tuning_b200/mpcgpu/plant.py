@@ -102,3 +102,56 @@ def cond_min(Km: np.ndarray, seed_x0: float = 0.1):
     res = minimize(fobj, x0, method="SLSQP", bounds=[(1e-6, 1.0)] * (m + n),
                    options={"maxiter": 500, "ftol": 1e-12})
     return res.x[:m].copy(), res.x[m:].copy(), float(res.fun)
+
+
+# ---------------------------------------------------------------------------------------------
+# General-order ingest: c2d(tf(num,den,'iodelay',theta),Ts,'zoh') and descompMPC
+# ---------------------------------------------------------------------------------------------
+def c2d_tf(num, den, theta: float, Ts: float):
+    """ZOH discretisation of  num(s)/den(s) * exp(-theta s)  of ANY order with a fractional dead time, what
+    `c2d(Ps,Ts,'zoh')` (Shell3x3.m:65, DTC_GPC_WW.m) returns for one channel: (bz, az, d) with
+        y(k) = -az[1] y(k-1) - ... + bz[0] u(k-d) + bz[1] u(k-d-1) + ...      (az[0] = 1),
+    d = ceil(theta/Ts) whole samples and the fraction f = d Ts - theta absorbed in the numerator (modified z-transform:
+    over one sample the delayed input is u(k-1) for f_bar = Ts - f seconds ... then u(k)), which adds one numerator tap.
+    For a first-order channel this is c2d_fopdt's closed form (tests/test_plant_kats.py)."""
+    from scipy.linalg import expm
+    from scipy.signal import tf2ss
+    num = np.atleast_1d(np.asarray(num, float)); den = np.atleast_1d(np.asarray(den, float))
+    A, B, Cc, D = tf2ss(num, den)
+    n = A.shape[0]
+    assert abs(D[0, 0]) == 0.0, "strictly proper channels only (every plant of the reference is)"
+    d = int(np.ceil(theta / Ts - 1e-12))
+    f = d * Ts - theta
+    if abs(f) < 1e-12:
+        f = 0.0
+
+    def phi_gamma(t):   # [Phi(t), Gamma(t)] = expm([[A, B], [0, 0]] t)
+        Mx = np.zeros((n + 1, n + 1)); Mx[:n, :n] = A; Mx[:n, n:] = B
+        E = expm(Mx * t)
+        return E[:n, :n], E[:n, n:]
+
+    Phi, Gam = phi_gamma(Ts)
+    # With v(t) = u(t - theta) the undelayed dynamics see u(k-d) during the first Ts - f seconds of sample k and u(k-d+1) during
+    # the last f seconds:  x(k+1) = Phi x(k) + G0 u(k-d) + G1 u(k-d+1),  G1 = Gamma(f),  G0 = Gamma(Ts) - Gamma(f).
+    _, G1 = phi_gamma(f)
+    G0 = Gam - G1
+    az = np.poly(Phi)                                 # 1, a1, ..., an
+
+    def num_of(G):                                    # C adj(zI - Phi) G = det(zI - Phi + G C) - det(zI - Phi): n coefficients
+        return (np.poly(Phi - G @ Cc) - az)[1:]
+    n0 = num_of(G0)
+    if f == 0.0:                                      # whole-sample delay: taps u(k-d-1) ... u(k-d-n), the plain c2d
+        return np.concatenate([[0.0], n0]), az, d
+    bz = np.zeros(n + 1)
+    bz[:n] += num_of(G1)                              # taps u(k-d) ... u(k-d-n+1)
+    bz[1:] += n0                                      # taps u(k-d-1) ... u(k-d-n)
+    return bz, az, d
+
+
+def descomp_mpc(bz, az, d: int):
+    """DTC-GPC/descompMPC.m:19-43 for one channel: numerator B, denominator A, delay; when the leading numerator
+    coefficient is non-zero the delay is reduced by one and a zero is prepended (:35-38)."""
+    bz = np.asarray(bz, float).copy()
+    if bz[0] != 0.0:
+        return np.concatenate([[0.0], bz]), np.asarray(az, float), d - 1
+    return bz, np.asarray(az, float), d

@@ -115,3 +115,36 @@ def test_cond_min_reaches_survey_condition_number():
     assert abs(c - 19.9495) < 2e-3
     from mpcgpu.problems import SHELL3X3_L, SHELL3X3_R
     assert abs(np.linalg.cond(np.diag(SHELL3X3_L) @ K @ np.diag(SHELL3X3_R)) - 19.9495) < 2e-3
+
+
+def test_general_order_c2d_with_fractional_delay():
+    """c2d(tf(num,den,'iodelay',theta),Ts,'zoh') for any order.  First order = the closed form the kernels
+    use (pinned to the reference's saved objects above); no delay = scipy's ZOH; fractional delay = a fine-grid continuous
+    simulation of the delayed transfer function."""
+    from scipy.signal import cont2discrete, lsim
+    from mpcgpu.plant import c2d_tf, c2d_fopdt, descomp_mpc
+    for K, tau, theta, Ts in ((4.05, 50.0, 27.0, 4.0), (12.8, 16.7, 1.0, 1.0), (3.8, 14.9, 8.1, 1.0), (7.2, 19.0, 0.0, 4.0)):
+        bz, az, d = c2d_tf([K], [tau, 1.0], theta, Ts)
+        ch = c2d_fopdt([[K]], [[tau]], [[theta]], Ts)
+        assert d == ch.d[0, 0]
+        np.testing.assert_allclose(bz, [ch.b0[0, 0], ch.b1[0, 0]], atol=1e-14)
+        np.testing.assert_allclose(az, [1.0, -ch.a[0, 0]], atol=1e-14)
+    num, den, Ts = [2.0, 1.0], [10.0, 7.0, 1.0], 0.5
+    bz, az, d = c2d_tf(num, den, 0.0, Ts)
+    nd, dd, _ = cont2discrete((num, den), Ts, method="zoh")
+    np.testing.assert_allclose(bz, nd.ravel(), atol=1e-13); np.testing.assert_allclose(az, dd, atol=1e-13)
+    theta = 1.3
+    bz, az, d = c2d_tf(num, den, theta, Ts)
+    assert d == 3 and len(bz) == 3
+    nit = 60
+    u = np.zeros(nit); u[2:] = 1.0; u[20:] = -0.5
+    y = np.zeros(nit)
+    for k in range(nit):
+        y[k] = -sum(az[i] * y[k - i] for i in range(1, len(az)) if k - i >= 0) + sum(bz[i] * u[k - d - i] for i in range(len(bz)) if k - d - i >= 0)
+    dt = 0.001
+    tt = np.arange(0, nit * Ts, dt)
+    uc = np.array([u[int(np.floor((x - theta) / Ts + 1e-9))] if x >= theta else 0.0 for x in tt])
+    _, yc, _ = lsim((num, den), uc, tt)
+    assert np.abs(y - yc[::int(round(Ts / dt))]).max() < 5e-4      # (the error is the reference simulation's grid)
+    B, A, dd2 = descomp_mpc(bz, az, d)                              # descompMPC.m:35-38: leading coefficient non-zero -> d-1, zero prepended
+    assert dd2 == d - 1 and B[0] == 0.0 and len(B) == len(bz) + 1
