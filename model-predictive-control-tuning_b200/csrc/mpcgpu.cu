@@ -413,6 +413,11 @@ extern "C" int mpcgpu_upload(mpcgpu_handle *h, int n, const int32_t *N, const in
             // a prediction horizon that barely clears the longest dead time tends to limit-cycle against the rate
             // limits: a constrained QP at every sample, among the longest runs of a population
             if (N[c] <= dead_max + 2) score[c] += 2.0;
+            // soft output bands (block-per-run kernel): the iteration count grows with the moves per prediction row -- a
+            // control horizon close to the prediction horizon makes the band QPs degenerate (hundreds of add/drop pivots per
+            // QP) -- and with small move weights; fitted on per-run cycle counters of 2048 Shell7x5 candidates
+            // (tools/diag_runs.py, DIAG_CASE=shell7x5: rank correlation 0.925 -> 0.94, list-schedule makespan 556 -> 524 ms)
+            if (L.has_ov_bounds) score[c] = 0.15 * Nu[c] + 1.15 * (double)Nu[c] / (double)N[c] - 0.09 * std::log10(lmin + 1e-300);
         }
         std::stable_sort(by_p[b].begin(), by_p[b].end(), [&](int x, int y) { return score[x] > score[y]; });
         mpcgpu_handle::Bucket bk{4 << b, mmax_p[b], (int)h->hOrder.size(), (int)by_p[b].size()};
