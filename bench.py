@@ -240,7 +240,7 @@ def run_reference(args):
 def other_workload(args):
     if args.config == "dtc":
         return (f"DTC-GPC sweep on Wood-Berry (BASELINE.json configs[3], DTC_GPC_WW.m:56-164): nit=200, population {args.pop} per GPU, "
-                "p_i~U{1..30}, m_j~U{1..min(p,10)}, delta, lambda log-uniform [1e-3,1e2], 256 distinct robustness filters, PCG64 seed 0")
+                "p_i~U{1..30}, m_j~U{1..min(p,10)}, delta, lambda log-uniform [1e-3,1e2], robustness filter (alfa, raio) per candidate designed on the device, PCG64 seed 0")
     return (f"Van de Vusse NMPC closed-loop evaluation (BASELINE.json configs[4], closedloop_toolbox_nmpc.m:36-97): nit=60, "
             f"population {args.pop} per GPU, N~U{{3..31}}, Nu~U{{2..15}}, delta, lambda log-uniform [1e-3,10], GAM cost, PCG64 seed 0")
 
@@ -267,9 +267,7 @@ def run_other(args):
     n_all = args.pop * (1 if ref else world)
     if args.config == "dtc":
         prob = mpcgpu.woodberry_dtc()
-        pop = mpcgpu.synthetic_dtc_population(prob, n_all, seed=0)
-        filt = [mpcgpu.mimo_filter(prob.pnz, float(a), float(r_)) for a, r_ in zip(pop[4][:256], pop[5][:256])]
-        filters = [filt[i % 256] for i in range(n_all)]
+        pop = mpcgpu.synthetic_dtc_population(prob, n_all, seed=0)   # (p, m, delta, lambda, alfa, raio): the robustness filter of every candidate is designed on the device
     else:
         prob = mpcgpu.vandevusse()
         pop = mpcgpu.synthetic_nmpc_population(prob, n_all, seed=0)
@@ -325,10 +323,9 @@ def run_other(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     if args.config == "dtc":
         ev = mpcgpu.DtcEvaluator(prob, device=local)
-        myf = filters[rank::world] if world > 1 else filters
-        call = lambda: ev.eval_batch(*mine[:4], filters=myf)
+        call = lambda: ev.eval_batch(*mine[:4], alfa=mine[4], raio=mine[5])
         width, key = 2, "ise"
-        h2d = n * (2 * 4 + 2 * 4 + 2 * 8 + 2 * 8 + 2 * 2 * 8 * 8 + 2 * 2 * 4)
+        h2d = n * (2 * 4 + 2 * 4 + 2 * 8 + 2 * 8 + 2 * 8)
     else:
         ev = mpcgpu.NmpcEvaluator(prob, device=local)
         call = lambda: ev.eval_batch(*mine, mode="gam")

@@ -219,6 +219,14 @@ void mpcgpu_dtc_destroy(mpcgpu_dtc_handle *h);
 int mpcgpu_dtc_eval_batch(mpcgpu_dtc_handle *h, int n, const int32_t *p, const int32_t *m, const double *delta,
                           const double *lambda, const double *fr_num, const double *fr_den, const int32_t *fr_len,
                           double *ise, double *y, double *u, int32_t *status);
+/* The same sweep with the robustness filter DESIGNED ON THE DEVICE per candidate from (alfa, raio)
+ * (/root/reference/DTC-GPC/mimofilter.m:33-50, filtro_siso.m:26-96: Dr = (z - alfa)^ns over the ns poles of the output's
+ * row model with |pole| >= raio, Nr = remainder of Dr z^d by (z - 1) prod(z - slow poles), d = the row's minimum dead
+ * time; no slow pole: Fr = 1).  alfa, raio: n.  A row model with slow poles and no dead time (the reference's system is
+ * under-determined there) flags the candidate MPCGPU_CAND_INVALID. */
+int mpcgpu_dtc_eval_batch_design(mpcgpu_dtc_handle *h, int n, const int32_t *p, const int32_t *m, const double *delta,
+                                 const double *lambda, const double *alfa, const double *raio, double *ise, double *y,
+                                 double *u, int32_t *status);
 int mpcgpu_dtc_get_counters(mpcgpu_dtc_handle *h, mpcgpu_counters *out); /* candidates, kernel_launches, last_sim_ms (device time of k_dtc) */
 const char *mpcgpu_dtc_last_error(mpcgpu_dtc_handle *h);
 /* Host-only (no CUDA call): the candidate-independent polynomial tables the sweep is built from -- step responses

@@ -35,6 +35,8 @@
  *     hd = mpcgpu_mex('dtc_create', Pd)                 Pd: struct with the fields of mpcgpu_dtc_problem
  *     [ise, status, y, u] = mpcgpu_mex('dtc_eval', hd, p, m, delta, lambda, fr_num, fr_den, fr_len)
  *                      p n x ny, m n x nu, fr_num / fr_den n x ny x MAXF, fr_len n x ny x 2 (MATLAB arrays, column-major)
+ *     [ise, status, y, u] = mpcgpu_mex('dtc_eval_design', hd, p, m, delta, lambda, alfa, raio)   the same with the robustness
+ *                      filter of every candidate designed on the device (mimofilter.m / filtro_siso.m), alfa, raio n x 1
  *     mpcgpu_mex('dtc_destroy', hd)
  */
 #include <math.h>
@@ -369,6 +371,32 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
         if (u) { plhs[3] = sig_out(u, n * nu, nit); mxFree(u); }
         mxFree(pc); mxFree(mc); mxFree(lc); mxFree(p); mxFree(m); mxFree(fl); mxFree(dl); mxFree(lm);
         mxFree(fn); mxFree(fd); mxFree(fn2); mxFree(fd2); mxFree(ise); mxFree(st);
+    } else if (!strcmp(cmd, "dtc_eval_design")) {   /* the sweep with the robustness filter designed on the device from (alfa, raio) */
+        ARG(nrhs == 8, "dtc_eval_design: (h, p, m, delta, lambda, alfa, raio)");
+        mpcgpu_dtc_handle *h = (mpcgpu_dtc_handle *)handle_of(prhs[1]);
+        const int ix = lookup(h);
+        ARG(ix >= 0, "unknown handle");
+        const mwSize ny = g_lin[ix].ny, nu = g_lin[ix].nu, n = mxGetM(prhs[2]);
+        const int nit = g_lin[ix].nd;
+        mwSize t_;
+        int32_t *pc = as_i32(prhs[2], &t_), *mc = as_i32(prhs[3], &t_);
+        int32_t *p = (int32_t *)mxMalloc(sizeof(int32_t) * n * ny), *m = (int32_t *)mxMalloc(sizeof(int32_t) * n * nu);
+        for (mwSize c = 0; c < n; ++c) {
+            for (mwSize i = 0; i < ny; ++i) p[c * ny + i] = pc[i * n + c];
+            for (mwSize j = 0; j < nu; ++j) m[c * nu + j] = mc[j * n + c];
+        }
+        double *dl = rows_of(prhs[4], n, ny), *lm = rows_of(prhs[5], n, nu);
+        ARG(mxIsDouble(prhs[6]) && mxIsDouble(prhs[7]) && mxGetNumberOfElements(prhs[6]) == n && mxGetNumberOfElements(prhs[7]) == n, "alfa, raio: n doubles each");
+        double *ise = (double *)mxMalloc(sizeof(double) * n * ny);
+        int32_t *st = (int32_t *)mxMalloc(sizeof(int32_t) * (n ? n : 1));
+        double *y = nlhs > 2 ? (double *)mxMalloc(sizeof(double) * n * ny * nit) : NULL;
+        double *u = nlhs > 3 ? (double *)mxMalloc(sizeof(double) * n * nu * nit) : NULL;
+        if (mpcgpu_dtc_eval_batch_design(h, (int)n, p, m, dl, lm, mxGetPr(prhs[6]), mxGetPr(prhs[7]), ise, y, u, st) != MPCGPU_OK)
+            mexErrMsgIdAndTxt("mpcgpu:eval", "%s", mpcgpu_dtc_last_error(h));
+        cost_out(nlhs > 1 ? 2 : 1, plhs, ise, st, n, ny);
+        if (y) { plhs[2] = sig_out(y, n * ny, nit); mxFree(y); }
+        if (u) { plhs[3] = sig_out(u, n * nu, nit); mxFree(u); }
+        mxFree(pc); mxFree(mc); mxFree(p); mxFree(m); mxFree(dl); mxFree(lm); mxFree(ise); mxFree(st);
     } else if (!strcmp(cmd, "dtc_destroy")) {
         void *h = handle_of(prhs[1]); forget(h); mpcgpu_dtc_destroy((mpcgpu_dtc_handle *)h);
     } else {

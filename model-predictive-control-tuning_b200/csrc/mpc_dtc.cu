@@ -406,11 +406,60 @@ extern "C" int mpcgpu_dtc_create(const mpcgpu_dtc_problem *problem, int device, 
     return MPCGPU_OK;
 }
 
-extern "C" int mpcgpu_dtc_eval_batch(mpcgpu_dtc_handle *h, int n, const int32_t *p, const int32_t *m, const double *delta,
-                                     const double *lambda, const double *fr_num, const double *fr_den,
-                                     const int32_t *fr_len, double *ise, double *y, double *u, int32_t *status) {
+
+// ------------------------------------------------------------------------------------------------
+// Batched robustness-filter design (DTC-GPC/mimofilter.m:33-50, filtro_siso.m:26-96): one thread per (candidate, output).
+// Fr = Nr/Dr with Dr = (z - alfa)^ns, ns = number of slow poles of the output's delay-free row model (|pole| >= raio), and
+// Nr = the remainder of Dr z^d by px = (z - 1) prod(z - slow poles): the reference's Sylvester system Dr z^d = Nr + px Q with
+// deg Nr < deg px, solved as the polynomial division it states (d = the row's minimum dead time >= 1).  No slow pole: Fr = 1.
+// Writes fr_num / fr_den (descending powers, zero padded to DTC_MAXF) and fr_len, the inputs of k_dtc.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_dtc_filter(const DtcLayout L, int n, const double *alfa, const double *raio, double *fr_num, double *fr_den,
+                             int *fr_len, int *status) {
+    const int item = blockIdx.x * blockDim.x + threadIdx.x;
+    if (item >= n * L.ny) return;
+    const int c = item / L.ny, i = item - c * L.ny;
+    double *num = fr_num + ((size_t)c * L.ny + i) * DTC_MAXF, *den = fr_den + ((size_t)c * L.ny + i) * DTC_MAXF;
+    for (int e = 0; e < DTC_MAXF; ++e) { num[e] = 0.0; den[e] = 0.0; }
+    double slow[DTC_MAXU];
+    int ns = 0, d = 1 << 30;
+    for (int j = 0; j < L.nu; ++j) {
+        const int ch = i * L.nu + j;
+        if (L.md[ch] < d) d = L.md[ch];                                    // Pd.iodelay of the row: its minimum dead time (mimofilter.m:25-29)
+        if (L.mb0[ch] + L.mb1[ch] != 0.0 && fabs(L.ma[ch]) >= raio[c]) slow[ns++] = L.ma[ch];
+    }
+    if (ns == 0) { num[0] = 1.0; den[0] = 1.0; fr_len[2 * item] = 1; fr_len[2 * item + 1] = 1; return; }   // filtro_siso.m:90-91
+    const int lpx = ns + 2;                                                  // px = (z - 1) prod (z - slow): degree ns + 1
+    if (d < 1 || lpx - 1 > DTC_MAXF || ns + 1 + d > 4 * DTC_MAXF) { fr_len[2 * item] = 0; fr_len[2 * item + 1] = 0; return; }   // k_dtc flags the candidate MPCGPU_CAND_INVALID
+    double px[DTC_MAXU + 2], Dr[DTC_MAXU + 1], w[4 * DTC_MAXF];
+    px[0] = 1.0; px[1] = -1.0;
+    for (int k = 0; k < ns; ++k) {                                           // px *= (z - slow_k)
+        px[k + 2] = 0.0;
+        for (int e = k + 2; e >= 1; --e) px[e] -= slow[k] * px[e - 1];
+    }
+    Dr[0] = 1.0;
+    for (int k = 0; k < ns; ++k) {                                           // Dr *= (z - alfa)
+        Dr[k + 1] = 0.0;
+        for (int e = k + 1; e >= 1; --e) Dr[e] -= alfa[c] * Dr[e - 1];
+    }
+    const int lw = ns + 1 + d;                                               // Dr z^d, descending powers
+    for (int e = 0; e < lw; ++e) w[e] = e <= ns ? Dr[e] : 0.0;
+    for (int e = 0; e + lpx <= lw; ++e) {                                    // long division by the monic px: the remainder is left in w's tail
+        const double qk = w[e];
+        for (int k2 = 0; k2 < lpx; ++k2) w[e + k2] -= qk * px[k2];
+    }
+    const int lr = lpx - 1;                                                  // deg Nr < deg px
+    for (int e = 0; e < lr; ++e) num[e] = lw >= lr ? w[lw - lr + e] : 0.0;
+    for (int e = 0; e <= ns; ++e) den[e] = Dr[e];
+    fr_len[2 * item] = lr; fr_len[2 * item + 1] = ns + 1;
+}
+
+static int dtc_eval_impl(mpcgpu_dtc_handle *h, int n, const int32_t *p, const int32_t *m, const double *delta,
+                         const double *lambda, const double *fr_num, const double *fr_den, const int32_t *fr_len,
+                         const double *alfa, const double *raio, double *ise, double *y, double *u, int32_t *status) {
     if (!h) return MPCGPU_ERR_ARG;
-    if (n < 0 || (n > 0 && (!p || !m || !delta || !lambda || !fr_num || !fr_den || !fr_len || !ise))) {
+    const bool design = alfa != nullptr;
+    if (n < 0 || (n > 0 && (!p || !m || !delta || !lambda || !ise || (design ? !raio : (!fr_num || !fr_den || !fr_len))))) {
         h->err = "bad population arguments";
         return MPCGPU_ERR_ARG;
     }
@@ -421,23 +470,32 @@ extern "C" int mpcgpu_dtc_eval_batch(mpcgpu_dtc_handle *h, int n, const int32_t 
     cudaStream_t s = h->stream;
     // one device arena for the whole call
     const size_t nI = (size_t)n * (ny + nu + 2 * ny + 1);
-    const size_t nD = (size_t)n * (ny + nu + 2 * ny * DTC_MAXF + ny) + (y ? (size_t)n * ny * nit : 0) + (u ? (size_t)n * nu * nit : 0);
+    const size_t nD = (size_t)n * (ny + nu + 2 * ny * DTC_MAXF + ny + 2) + (y ? (size_t)n * ny * nit : 0) + (u ? (size_t)n * nu * nit : 0);
     int *dI = nullptr;
     double *dD = nullptr;
     DCK(cudaMalloc((void **)&dI, sizeof(int) * nI));
     if (cudaMalloc((void **)&dD, sizeof(double) * nD) != cudaSuccess) { cudaFree(dI); h->err = "cudaMalloc failed"; return MPCGPU_ERR_CUDA; }
     int *dp = dI, *dm = dp + (size_t)n * ny, *dfl = dm + (size_t)n * nu, *dst = dfl + (size_t)n * 2 * ny;
     double *ddl = dD, *dlm = ddl + (size_t)n * ny, *dfn = dlm + (size_t)n * nu, *dfd = dfn + (size_t)n * ny * DTC_MAXF;
-    double *dise = dfd + (size_t)n * ny * DTC_MAXF, *dy = dise + (size_t)n * ny, *du = dy + (y ? (size_t)n * ny * nit : 0);
+    double *dise = dfd + (size_t)n * ny * DTC_MAXF, *dal = dise + (size_t)n * ny, *dra = dal + n, *dy = dra + n, *du = dy + (y ? (size_t)n * ny * nit : 0);
     int rc = MPCGPU_OK;
     auto ck = [&](cudaError_t e2) { if (e2 != cudaSuccess && rc == MPCGPU_OK) { h->err = cudaGetErrorString(e2); rc = MPCGPU_ERR_CUDA; } };
     ck(cudaMemcpyAsync(dp, p, sizeof(int) * (size_t)n * ny, cudaMemcpyHostToDevice, s));
     ck(cudaMemcpyAsync(dm, m, sizeof(int) * (size_t)n * nu, cudaMemcpyHostToDevice, s));
-    ck(cudaMemcpyAsync(dfl, fr_len, sizeof(int) * (size_t)n * 2 * ny, cudaMemcpyHostToDevice, s));
+    ck(cudaMemsetAsync(dst, 0, sizeof(int) * (size_t)n, s));
+    if (!design) ck(cudaMemcpyAsync(dfl, fr_len, sizeof(int) * (size_t)n * 2 * ny, cudaMemcpyHostToDevice, s));
     ck(cudaMemcpyAsync(ddl, delta, sizeof(double) * (size_t)n * ny, cudaMemcpyHostToDevice, s));
     ck(cudaMemcpyAsync(dlm, lambda, sizeof(double) * (size_t)n * nu, cudaMemcpyHostToDevice, s));
-    ck(cudaMemcpyAsync(dfn, fr_num, sizeof(double) * (size_t)n * ny * DTC_MAXF, cudaMemcpyHostToDevice, s));
-    ck(cudaMemcpyAsync(dfd, fr_den, sizeof(double) * (size_t)n * ny * DTC_MAXF, cudaMemcpyHostToDevice, s));
+    if (design) {   // the filters are designed on the device from (alfa, raio): 16 B per candidate instead of 2 ny MAXF doubles
+        ck(cudaMemcpyAsync(dal, alfa, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, s));
+        ck(cudaMemcpyAsync(dra, raio, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, s));
+        k_dtc_filter<<<(n * ny + 127) / 128, 128, 0, s>>>(L, n, dal, dra, dfn, dfd, dfl, dst);
+        ck(cudaGetLastError());
+        h->cnt.kernel_launches += 1;
+    } else {
+        ck(cudaMemcpyAsync(dfn, fr_num, sizeof(double) * (size_t)n * ny * DTC_MAXF, cudaMemcpyHostToDevice, s));
+        ck(cudaMemcpyAsync(dfd, fr_den, sizeof(double) * (size_t)n * ny * DTC_MAXF, cudaMemcpyHostToDevice, s));
+    }
     if (rc == MPCGPU_OK) {
         DtcCand Cd{dp, dm, ddl, dlm, dfn, dfd, dfl, dise, y ? dy : nullptr, u ? du : nullptr, dst};
         DtcTables T{h->dStep, h->dF, h->dUg, h->dR, h->dQ, h->ht.step_len};
@@ -460,6 +518,20 @@ extern "C" int mpcgpu_dtc_eval_batch(mpcgpu_dtc_handle *h, int n, const int32_t 
     }
     cudaFree(dI); cudaFree(dD);
     return rc;
+}
+
+extern "C" int mpcgpu_dtc_eval_batch(mpcgpu_dtc_handle *h, int n, const int32_t *p, const int32_t *m, const double *delta,
+                                     const double *lambda, const double *fr_num, const double *fr_den,
+                                     const int32_t *fr_len, double *ise, double *y, double *u, int32_t *status) {
+    return dtc_eval_impl(h, n, p, m, delta, lambda, fr_num, fr_den, fr_len, nullptr, nullptr, ise, y, u, status);
+}
+
+// The sweep with the robustness filter designed on the device from (alfa, raio) per candidate (mimofilter.m / filtro_siso.m)
+extern "C" int mpcgpu_dtc_eval_batch_design(mpcgpu_dtc_handle *h, int n, const int32_t *p, const int32_t *m, const double *delta,
+                                            const double *lambda, const double *alfa, const double *raio, double *ise, double *y,
+                                            double *u, int32_t *status) {
+    if (!alfa || !raio) { if (h) h->err = "alfa / raio missing"; return MPCGPU_ERR_ARG; }
+    return dtc_eval_impl(h, n, p, m, delta, lambda, nullptr, nullptr, nullptr, alfa, raio, ise, y, u, status);
 }
 
 extern "C" int mpcgpu_dtc_get_counters(mpcgpu_dtc_handle *h, mpcgpu_counters *out) {

@@ -106,6 +106,7 @@ def load_library():
     lib.mpcgpu_dtc_destroy.argtypes = [C.c_void_p]
     lib.mpcgpu_dtc_destroy.restype = None
     lib.mpcgpu_dtc_eval_batch.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 11
+    lib.mpcgpu_dtc_eval_batch_design.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 10
     lib.mpcgpu_dtc_host_tables.argtypes = [C.c_void_p] * 5
     lib.mpcgpu_dtc_get_counters.argtypes = [C.c_void_p, C.POINTER(Counters)]
     lib.mpcgpu_nmpc_last_error.restype = C.c_char_p
@@ -126,7 +127,7 @@ EXPORTED_SYMBOLS = [
     "mpcgpu_create_multi", "mpcgpu_destroy_multi", "mpcgpu_multi_device_count", "mpcgpu_multi_set_option",
     "mpcgpu_multi_set_signals", "mpcgpu_multi_eval_batch", "mpcgpu_multi_get_counters", "mpcgpu_multi_last_error",
     "mpcgpu_work_estimate",
-    "mpcgpu_dtc_create", "mpcgpu_dtc_destroy", "mpcgpu_dtc_eval_batch", "mpcgpu_dtc_last_error",
+    "mpcgpu_dtc_create", "mpcgpu_dtc_destroy", "mpcgpu_dtc_eval_batch", "mpcgpu_dtc_eval_batch_design", "mpcgpu_dtc_last_error",
     "mpcgpu_dtc_host_tables", "mpcgpu_dtc_get_counters",
     "mpcgpu_nmpc_create", "mpcgpu_nmpc_destroy", "mpcgpu_nmpc_eval_batch", "mpcgpu_nmpc_get_counters", "mpcgpu_nmpc_last_error",
 ]

@@ -161,13 +161,29 @@ class DtcEvaluator:
                 ln[c, i] = (len(Nr), len(Dr))
         return num, den, ln
 
-    def eval_batch(self, p, m, delta, lam, alfa=None, raio=None, filters=None, traj=False):
-        """p: n x ny, m: n x nu, delta: n x ny, lam: n x nu; either (alfa, raio) per candidate -- the filter is
-        then designed here with `mimo_filter` -- or explicit `filters`.  Returns dict(ise, status[, y, u])."""
+    def eval_batch(self, p, m, delta, lam, alfa=None, raio=None, filters=None, traj=False, design_on_device=True):
+        """p: n x ny, m: n x nu, delta: n x ny, lam: n x nu; either (alfa, raio) per candidate -- the robustness filter is then
+        designed per candidate ON THE DEVICE (mpcgpu_dtc_eval_batch_design: mimofilter.m / filtro_siso.m as a batched op;
+        design_on_device=False: on the host with `mimo_filter`) -- or explicit `filters`.  Returns dict(ise, status[, y, u])."""
         p = np.ascontiguousarray(np.atleast_2d(p), dtype=np.int32); n = p.shape[0]
         m = np.ascontiguousarray(np.atleast_2d(m), dtype=np.int32)
         delta = np.ascontiguousarray(delta, dtype=np.float64).reshape(n, self.ny)
         lam = np.ascontiguousarray(lam, dtype=np.float64).reshape(n, self.nu)
+        if filters is None and design_on_device:
+            al = np.ascontiguousarray(np.broadcast_to(np.asarray(alfa, float), (n,)))
+            ra = np.ascontiguousarray(np.broadcast_to(np.asarray(raio, float), (n,)))
+            ise = np.empty((n, self.ny)); status = np.zeros(n, dtype=np.int32)
+            y = np.empty((n, self.ny, self.nit)) if traj else None
+            u = np.empty((n, self.nu, self.nit)) if traj else None
+            ptr = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None else None
+            rc = self.lib.mpcgpu_dtc_eval_batch_design(self.h, n, ptr(p), ptr(m), ptr(delta), ptr(lam), ptr(al), ptr(ra),
+                                                       ptr(ise), ptr(y), ptr(u), ptr(status))
+            if rc != 0:
+                raise self._err(f"mpcgpu_dtc_eval_batch_design failed ({rc}): {self.lib.mpcgpu_dtc_last_error(self.h).decode()}")
+            out = {"ise": ise, "status": status}
+            if traj:
+                out.update(y=y, u=u)
+            return out
         if filters is None:
             # the design depends on (alfa, raio) only through which poles count as slow: design once per distinct pair
             alfa = np.broadcast_to(np.asarray(alfa, float), (n,)); raio = np.broadcast_to(np.asarray(raio, float), (n,))

@@ -487,3 +487,24 @@ def test_two_phase_mode_on_limit_cycles(ev3, monkeypatch):
     check_cost(cost["1"], g0, sens, "shell3x3 limit cycles", min_strict=0.0)
     check_cost(cost["0"], g0, sens, "shell3x3 limit cycles, mode off", min_strict=0.0)
     check_cost(cost["1"], cost["0"], sens, "shell3x3 limit cycles, mode on vs off", min_strict=0.0)
+
+
+def test_dtc_filter_design_on_device():
+    """the robustness filter of every candidate designed on the device from (alfa, raio)
+    (mimofilter.m:33-50, filtro_siso.m:26-96 as a batched op) gives the sweep the host design gives."""
+    from mpcgpu.dtcgpc import woodberry_dtc, synthetic_dtc_population, DtcEvaluator
+    prob = woodberry_dtc(deltak=0.1, deltaL=1.0)
+    ev = DtcEvaluator(prob, device=0)
+    p, m, dl, lm, alfa, raio = synthetic_dtc_population(prob, 512, seed=3)
+    raio[:64] = 0.999      # no pole counts as slow: Fr = 1
+    raio[64:128] = 0.5     # every pole does
+    a = ev.eval_batch(p, m, dl, lm, alfa=alfa, raio=raio, design_on_device=False, traj=True)
+    b = ev.eval_batch(p, m, dl, lm, alfa=alfa, raio=raio, design_on_device=True, traj=True)
+    assert np.array_equal(a["status"], b["status"])
+    ok = a["status"] == 0
+    assert ok.sum() > 400
+    stable = ok & np.isfinite(a["ise"]).all(axis=1) & (np.abs(a["y"]).max(axis=(1, 2)) < 1e3)
+    rel = np.abs(a["ise"][stable] - b["ise"][stable]) / np.maximum(np.abs(a["ise"][stable]), 1e-300)
+    assert rel.max() < 1e-9, rel.max()
+    assert np.abs(a["y"][stable] - b["y"][stable]).max() < 1e-8
+    ev.close()
