@@ -74,7 +74,7 @@ def shard_of(prob, Ng, Nug, dg, lg, world, rank):
     from mpcgpu.distributed import shard_indices, work_estimate
     if world == 1:
         return np.arange(len(Ng))
-    work = work_estimate(Ng, Nug, dg, lg, dead_max=int(prob.plant.d.max()))
+    work = work_estimate(Ng, Nug, dg, lg, dead_max=int(prob.plant.d.max()), soft=bool(np.isfinite(prob.ymin).any() or np.isfinite(prob.ymax).any()))
     return shard_indices(len(Ng), world, rank, work)
 
 

@@ -358,6 +358,20 @@ extern "C" int mpcgpu_set_signals(mpcgpu_handle *h, int nit, const double *r, co
     return upload_signals(h);
 }
 
+// A-priori work key of a candidate: what launches are ordered by (heaviest first) and what both multi-GPU front ends deal
+// shards by.  Hard MV limits: the number of moves and how hard the controller pushes against the limits (large delta / small
+// lambda), plus the short-horizon family that limit-cycles (N barely beyond the longest dead time: a QP at every sample).
+// Soft output bands (block-per-run kernel): the iteration count grows with the moves per prediction row -- a control horizon
+// close to the prediction horizon makes the band QPs degenerate -- and with small move weights; fitted on per-run cycle counters
+// of 2048 Shell7x5 candidates (tools/diag_runs.py DIAG_CASE=shell7x5: rank correlation 0.94, list-schedule makespan 556 -> 524 ms).
+static double mpc_work_key(int ny, int nu, bool soft, int dead_max, int N, int Nu, const double *delta, const double *lambda) {
+    double dmax = 0.0, lmin = 1e300;
+    for (int i = 0; i < ny; ++i) dmax = std::max(dmax, std::fabs(delta[i]));
+    for (int j = 0; j < nu; ++j) lmin = std::min(lmin, std::fabs(lambda[j]));
+    if (soft) return 0.15 * Nu + 1.15 * (double)Nu / (double)N - 0.09 * std::log10(lmin + 1e-300);
+    return std::log10(dmax / (lmin + 1e-300) + 1e-300) + 0.15 * Nu + (N <= dead_max + 2 ? 2.0 : 0.0);
+}
+
 extern "C" int mpcgpu_upload(mpcgpu_handle *h, int n, const int32_t *N, const int32_t *Nu, const double *delta,
                              const double *lambda) {
     if (!h) return MPCGPU_ERR_ARG;
@@ -405,20 +419,7 @@ extern "C" int mpcgpu_upload(mpcgpu_handle *h, int n, const int32_t *N, const in
         std::vector<double> score(n, 0.0);
         int dead_max = 0;
         for (int ch = 0; ch < L.ny * L.nw; ++ch) dead_max = std::max(dead_max, (int)L.d[ch]);
-        for (int c : by_p[b]) {
-            double dmax = 0.0, lmin = 1e300;
-            for (int i = 0; i < ny; ++i) dmax = std::max(dmax, std::fabs(delta[(size_t)c * ny + i]));
-            for (int j = 0; j < nu; ++j) lmin = std::min(lmin, std::fabs(lambda[(size_t)c * nu + j]));
-            score[c] = std::log10(dmax / (lmin + 1e-300) + 1e-300) + 0.15 * Nu[c];
-            // a prediction horizon that barely clears the longest dead time tends to limit-cycle against the rate
-            // limits: a constrained QP at every sample, among the longest runs of a population
-            if (N[c] <= dead_max + 2) score[c] += 2.0;
-            // soft output bands (block-per-run kernel): the iteration count grows with the moves per prediction row -- a
-            // control horizon close to the prediction horizon makes the band QPs degenerate (hundreds of add/drop pivots per
-            // QP) -- and with small move weights; fitted on per-run cycle counters of 2048 Shell7x5 candidates
-            // (tools/diag_runs.py, DIAG_CASE=shell7x5: rank correlation 0.925 -> 0.94, list-schedule makespan 556 -> 524 ms)
-            if (L.has_ov_bounds) score[c] = 0.15 * Nu[c] + 1.15 * (double)Nu[c] / (double)N[c] - 0.09 * std::log10(lmin + 1e-300);
-        }
+        for (int c : by_p[b]) score[c] = mpc_work_key(ny, nu, L.has_ov_bounds != 0, dead_max, N[c], Nu[c], delta + (size_t)c * ny, lambda + (size_t)c * nu);
         std::stable_sort(by_p[b].begin(), by_p[b].end(), [&](int x, int y) { return score[x] > score[y]; });
         mpcgpu_handle::Bucket bk{4 << b, mmax_p[b], (int)h->hOrder.size(), (int)by_p[b].size()};
         h->hOrder.insert(h->hOrder.end(), by_p[b].begin(), by_p[b].end());
@@ -783,12 +784,10 @@ extern "C" int mpcgpu_work_estimate(const mpcgpu_problem *pb, int n, const int32
     if (!pb || !N || !Nu || !delta || !lambda || !work) return MPCGPU_ERR_ARG;
     int dead_max = 0;
     for (int ch = 0; ch < pb->ny * (pb->nu + pb->nd); ++ch) dead_max = std::max(dead_max, (int)pb->d[ch]);
-    for (int c = 0; c < n; ++c) {
-        double dmax = 0.0, lmin = 1e300;
-        for (int i = 0; i < pb->ny; ++i) dmax = std::max(dmax, std::fabs(delta[(size_t)c * pb->ny + i]));
-        for (int j = 0; j < pb->nu; ++j) lmin = std::min(lmin, std::fabs(lambda[(size_t)c * pb->nu + j]));
-        work[c] = std::log10(dmax / (lmin + 1e-300) + 1e-300) + 0.15 * Nu[c] + (N[c] <= dead_max + 2 ? 2.0 : 0.0);
-    }
+    bool soft = false;
+    for (int i = 0; i < pb->ny; ++i) soft = soft || (pb->ymin && std::isfinite(pb->ymin[i])) || (pb->ymax && std::isfinite(pb->ymax[i]));
+    for (int c = 0; c < n; ++c)
+        work[c] = mpc_work_key(pb->ny, pb->nu, soft, dead_max, N[c], Nu[c], delta + (size_t)c * pb->ny, lambda + (size_t)c * pb->nu);
     return MPCGPU_OK;
 }
 extern "C" int mpcgpu_multi_eval_batch(mpcgpu_multi *m, int n, const int32_t *N, const int32_t *Nu, const double *delta,
@@ -804,12 +803,8 @@ extern "C" int mpcgpu_multi_eval_batch(mpcgpu_multi *m, int n, const int32_t *N,
     {
         int dead_max = 0;
         for (int ch = 0; ch < ny * L.nw; ++ch) dead_max = std::max(dead_max, (int)L.d[ch]);
-        for (int c = 0; c < n; ++c) {
-            double dmax = 0.0, lmin = 1e300;
-            for (int i = 0; i < ny; ++i) dmax = std::max(dmax, std::fabs(delta[(size_t)c * ny + i]));
-            for (int j = 0; j < nu; ++j) lmin = std::min(lmin, std::fabs(lambda[(size_t)c * nu + j]));
-            work[c] = std::log10(dmax / (lmin + 1e-300) + 1e-300) + 0.15 * Nu[c] + (N[c] <= dead_max + 2 ? 2.0 : 0.0);
-        }
+        for (int c = 0; c < n; ++c)
+            work[c] = mpc_work_key(ny, nu, L.has_ov_bounds != 0, dead_max, N[c], Nu[c], delta + (size_t)c * ny, lambda + (size_t)c * nu);
     }
     std::vector<int> order(n);
     for (int c = 0; c < n; ++c) order[c] = c;

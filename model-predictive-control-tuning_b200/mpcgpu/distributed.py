@@ -10,11 +10,14 @@ from __future__ import annotations
 import numpy as np
 
 
-def work_estimate(N, Nu, delta, lam, dead_max=None):
+def work_estimate(N, Nu, delta, lam, dead_max=None, soft=False):
     """Relative cost of a candidate: moves, how hard it pushes on the MV limits, and -- when the plant's longest dead
     time `dead_max` is given -- the bonus for prediction horizons that barely clear it (those tunings limit-cycle: a
-    QP at every sample).  The same key the library uses to order launches and to deal shards (mpcgpu_work_estimate)."""
+    QP at every sample).  soft=True: plants with soft output bands (moves per prediction row, smallest move weight).
+    The same key the library uses to order launches and to deal shards (mpc_work_key in csrc/mpcgpu.cu, mpcgpu_work_estimate)."""
     delta = np.abs(np.asarray(delta, float)); lam = np.abs(np.asarray(lam, float))
+    if soft:
+        return 0.15 * np.asarray(Nu, float) + 1.15 * np.asarray(Nu, float) / np.asarray(N, float) - 0.09 * np.log10(lam.min(axis=1) + 1e-300)
     w = np.log10(delta.max(axis=1) / (lam.min(axis=1) + 1e-300) + 1e-300) + 0.15 * np.asarray(Nu, float)
     if dead_max is not None:
         w = w + 2.0 * (np.asarray(N) <= int(dead_max) + 2)
@@ -27,7 +30,7 @@ def shard_indices(n: int, world: int, rank: int, work=None) -> np.ndarray:
     return order[rank::world]
 
 
-def evaluate_sharded(evaluate, N, Nu, delta, lam, mode="gam", group=None, device=None, dead_max=None):
+def evaluate_sharded(evaluate, N, Nu, delta, lam, mode="gam", group=None, device=None, dead_max=None, soft=False):
     """evaluate(N, Nu, delta, lam, mode) -> cost array for a shard (an `Evaluator.eval_batch` wrapper).
     Returns the full-population cost on every rank (n x ny for 'gam', n for 'vns').
     `group`: torch.distributed process group (None: default group; not initialised: single rank)."""
@@ -38,7 +41,7 @@ def evaluate_sharded(evaluate, N, Nu, delta, lam, mode="gam", group=None, device
     if not (dist.is_available() and dist.is_initialized()):
         return np.asarray(evaluate(N, Nu, delta, lam, mode))
     world, rank = dist.get_world_size(group), dist.get_rank(group)
-    work = work_estimate(N, Nu, delta, lam, dead_max)
+    work = work_estimate(N, Nu, delta, lam, dead_max, soft)
     if device is None and dist.get_backend(group) == "nccl":
         device = torch.device("cuda", torch.cuda.current_device())
     mine = shard_indices(n, world, rank, work)
