@@ -213,3 +213,46 @@ def test_mismatch_validation_run(case):
     back = ev.eval_batch(N, Nu, dl, lm, mode="gam", traj=True)
     assert np.array_equal(back["y"], nominal["y"]) and np.array_equal(back["cost"], nominal["cost"])
     ev.close()
+
+
+def test_more_edge_cases(ev3):
+    """Populations the optimiser can produce at the corners: nothing legal, one candidate, sizes that grow and shrink between
+    calls (buffer reuse), weights at the search's lower bound (MPCTuning.m:302: 1e-5) on the largest horizons, a per-call
+    horizon of the simulation shorter than the handle's, and empty populations on the other two evaluators."""
+    p = ev3.prob
+    op = orc.OracleProblem(p)
+    bad = ev3.eval_batch([3, 200, 9], [5, 2, 0], np.ones((3, 3)), np.ones((3, 3)), mode="gam")
+    assert list(bad["status"]) == [4, 4, 4] and np.isnan(bad["cost"]).all()
+    badv = ev3.eval_batch([3, 200], [5, 2], np.ones((2, 3)), np.ones((2, 3)), mode="vns")
+    assert list(badv["status"]) == [4, 4] and np.isnan(badv["cost"]).all()
+    N, Nu, dl, lm = synthetic_population(p, 5000, seed=21)
+    one = ev3.eval_batch(N[:1], Nu[:1], dl[:1], lm[:1], mode="gam")
+    big = ev3.eval_batch(N, Nu, dl, lm, mode="gam")
+    few = ev3.eval_batch(N[:3], Nu[:3], dl[:3], lm[:3], mode="gam")
+    assert np.array_equal(one["cost"][0], big["cost"][0]) and np.array_equal(few["cost"], big["cost"][:3])
+    # lower-bound weights on the largest horizons: cond(H) at its worst, every limit active
+    Nc = np.array([127, 127, 64], dtype=np.int32); Nuc = np.array([15, 2, 15], dtype=np.int32)
+    dlc = np.array([[1e-5] * 3, [10.0] * 3, [1.0, 1e-5, 10.0]]); lmc = np.array([[1e-5] * 3, [1e-5] * 3, [1e-5, 10.0, 1e-5]])
+    out = ev3.eval_batch(Nc, Nuc, dlc, lmc, mode="gam", traj=True)
+    g0, st0, _ = orc.eval_batch(op, Nc, Nuc, dlc, lmc, "gam")
+    assert (out["status"] == 0).all() and (st0 == 0).all() and np.isfinite(out["cost"]).all()
+    assert (out["u"] >= p.umin[None, :, None] - 1e-9).all() and (out["u"] <= p.umax[None, :, None] + 1e-9).all()
+    assert (np.abs(np.diff(out["u"], axis=2)) <= np.maximum(-p.dumin, p.dumax)[None, :, None] + 1e-9).all()
+    summ = parity.summary(out["cost"], out["status"], g0, st0, parity.sensitivity(op, Nc, Nuc, dlc, lmc, "gam", g0))
+    assert summ["n_out_of_tolerance"] == 0, summ
+    # per-call simulation length shorter than the handle's (closedloop_toolbox.m:1 takes nit per call)
+    nit2 = 120
+    y, u, t_, ys, uopt = mpcgpu.closedloop_toolbox(ev3, p.r[:nit2] / p.L[None, :] * p.L[None, :], np.zeros((nit2, 0)), 24, 6, dl[0], lm[0], nit2)
+    full = ev3.eval_batch([24], [6], dl[:1], lm[:1], mode="raw")
+    assert y.shape == (3, nit2) and np.abs(y - full["y"][0][:, :nit2]).max() < 1e-12      # causal: the first 120 samples do not depend on the rest
+    # empty populations on the other evaluators
+    from mpcgpu.nmpc import vandevusse, NmpcEvaluator
+    from mpcgpu.dtcgpc import woodberry_dtc, DtcEvaluator
+    en = NmpcEvaluator(vandevusse(), device=0)
+    e0 = en.eval_batch(np.zeros(0, np.int32), np.zeros(0, np.int32), np.zeros((0, 2)), np.zeros((0, 2)), mode="gam")
+    assert e0["cost"].shape == (0, 2)
+    en.close()
+    ed = DtcEvaluator(woodberry_dtc(), device=0)
+    d0 = ed.eval_batch(np.zeros((0, 2), np.int32), np.zeros((0, 2), np.int32), np.zeros((0, 2)), np.zeros((0, 2)), alfa=np.zeros(0), raio=np.zeros(0))
+    assert d0["ise"].shape == (0, 2)
+    ed.close()
