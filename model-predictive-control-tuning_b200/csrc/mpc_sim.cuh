@@ -374,7 +374,8 @@ SIM_COLD void sim_remove_nospill(double *V, double *Li, int *act, double *mu, do
 // SPILL: factor rows beyond QC live in a per-run global scratch; without it a QP that needs more than QC active
 // constraints returns status SIM_ST_OVERFLOW and the host re-runs the candidate on the kernel with the spill area.
 #define SIM_ST_OVERFLOW 6
-template <int NU, int P, bool SPILL = true>
+// MSM: M lives in shared memory (plain loads) instead of global memory (read-only path)
+template <int NU, int P, bool SPILL = true, bool MSM = false>
 struct SimWarp {
     static constexpr int R = NU * P;
     static constexpr int NSLOT = (R + 31) / 32;
@@ -928,7 +929,7 @@ struct SimWarp {
                 for (int e = 0; e < SIM_MB; ++e)
 #pragma unroll
                     for (int s = 0; s < NSLOT; ++s)
-                        mv[e][s] = (valid[s] && sg + e < nst) ? __ldg(mp + (size_t)(sg + e) * R + s * 32) : 0.0;   // padded rows of M are zero: not fetched
+                        mv[e][s] = (valid[s] && sg + e < nst) ? (MSM ? mp[(size_t)(sg + e) * R + s * 32] : __ldg(mp + (size_t)(sg + e) * R + s * 32)) : 0.0;   // padded rows of M are zero: not fetched
 #pragma unroll
                 for (int e = 0; e < SIM_MB; e += 2) {
                     const double s0 = sg + e < nst ? sm.st[sg + e] : 0.0, s1 = sg + e + 1 < nst ? sm.st[sg + e + 1] : 0.0;

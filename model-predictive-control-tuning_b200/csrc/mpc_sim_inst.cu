@@ -42,6 +42,7 @@ sim_kernel_t SIM_CAT(sim_spec_nu, SIM_NU)(int variant) {
         case 0: return k_sim<SIM_NU, 16, false, false, true>;
         case 1: return k_sim<SIM_NU, 16, true, false, true>;
         case 2: return k_sim<SIM_NU, 16, false, true, true>;
+        case 3: return k_sim<SIM_NU, 16, true, false, true, true>;   // small, tail-bound populations: M in shared memory
     }
     return nullptr;
 }

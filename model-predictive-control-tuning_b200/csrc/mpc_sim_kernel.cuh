@@ -36,7 +36,7 @@ struct DevOut {
 
 // One warp per (candidate, run).  mode: 0 RAW, 1 GAM, 2 VNS.
 // SPEC: lane-resident state + speculative unconstrained stretches (mpc_sim_spec.cuh; plants with nst <= 32).
-template <int NU, int P, bool LEAN = false, bool VLEAN = false, bool SPEC = false>
+template <int NU, int P, bool LEAN = false, bool VLEAN = false, bool SPEC = false, bool MSM = false>
 #ifndef SIM_SPEC_MINB
 #define SIM_SPEC_MINB 12   /* resident runs per SM the speculative kernel's register budget is sized for */
 #endif
@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(32, SPEC ? SIM_SPEC_MINB : 1) k_sim(const MpcL
     const int sel = mode == 2 ? (square ? run : -1) : -2;
     double *gscr = C.scratch ? C.scratch + (size_t)(item0 + item) * C.scratch_stride : nullptr;
     double *pslot = C.slot ? C.slot + (size_t)(item0 + item) * C.slot_stride : nullptr;
-    const int st = SPEC ? sim_run_spec<NU, P, LEAN, VLEAN>(L, T, m, C.M + C.offM[c], C.W + C.offW[c], mode, sel, smem_s, gscr, out, pslot)
+    const int st = SPEC ? sim_run_spec<NU, P, LEAN, VLEAN, MSM>(L, T, m, C.M + C.offM[c], C.W + C.offW[c], mode, sel, smem_s, gscr, out, pslot)
                         : sim_run<NU, P, LEAN, VLEAN>(L, T, m, C.M + C.offM[c], C.W + C.offW[c], mode, sel, smem_s, gscr, out, pslot);
     if (st != 0 && (threadIdx.x & 31) == 0) atomicMax(stat + c, st);
     if (out.diag && (threadIdx.x & 31) == 0) out.diag[3] = (unsigned long long)(clock64() - t_start);
@@ -133,7 +133,7 @@ sim_kernel_t sim_vlean_nu1(int P);
 sim_kernel_t sim_vlean_nu2(int P);
 sim_kernel_t sim_vlean_nu3(int P);
 sim_kernel_t sim_vlean_nu4(int P);
-sim_kernel_t sim_spec_nu1(int variant);   // variant 0 full, 1 GAM cost-only, 2 VNS cost-only; P = 16 image only
+sim_kernel_t sim_spec_nu1(int variant);   // variant 0 full, 1 GAM cost-only, 2 VNS cost-only, 3 GAM cost-only with M in shared memory; P = 16 image only
 sim_kernel_t sim_spec_nu2(int variant);
 sim_kernel_t sim_spec_nu3(int variant);
 sim_kernel_t sim_spec_nu4(int variant);

@@ -83,8 +83,12 @@ static MPC_HD bool sim_spec_ok(const MpcLayout &L) {
     return L.nst <= 32 && L.ny * L.nw <= 32 && L.nw * sim_hl(L) <= SIM_SPEC_HMAX && 2 * L.ny + L.nd <= SIM_SPEC_NSIG && SIM_SPEC_T <= 8;
 }
 static MPC_HD size_t sim_spec_smem_doubles(const MpcLayout &, int nu, int P, bool lean = false) { return (size_t)sim_spec_layout(nu, P, lean).total; }
+// MSM image: + M itself (32 columns of R rows) behind the base layout
+static MPC_HD size_t sim_spec_msm_doubles(int nu, int P) { return (size_t)32 * nu * P; }
 
-template <int NU, int P, bool LEAN = false, bool VLEAN = false>
+// MSM: M is copied to shared memory at the start of the run (12 KB for Shell3x3).  For SMALL populations only, whose launch
+// keeps few runs per SM anyway: 9.82 -> 9.50 ms on 4096 candidates, but 23.4 -> 26.1 ms on 16384 where residency counts.
+template <int NU, int P, bool LEAN = false, bool VLEAN = false, bool MSM = false>
 __device__ __forceinline__ int sim_run_spec(const MpcLayout &L, const MpcTables &T, int m, const double *__restrict__ Mg,
                                             const double *__restrict__ Wg, int mode_arg, int sel, double *smem, double *gscr,
                                             const MpcRunOut &out_arg, double *pslot = nullptr) {
@@ -100,7 +104,7 @@ __device__ __forceinline__ int sim_run_spec(const MpcLayout &L, const MpcTables 
     const int ny = L.ny, nd = L.nd, nw = L.nw, nch = ny * nw, nst = L.nst, nit = L.nit;
     const int HL = sim_hl(L);
     const int nsig = 2 * ny + nd;
-    SimWarp<NU, P, false> wp(L);   // no spill area: a QP beyond QC active constraints -> SIM_ST_OVERFLOW
+    SimWarp<NU, P, false, MSM> wp(L);   // no spill area: a QP beyond QC active constraints -> SIM_ST_OVERFLOW
     SimSm &sm = wp.sm;
     double *const stb = smem + O.vli + O.stb, *const ub = smem + O.vli + O.ub, *const zlog = smem + O.vli + O.zlog;
     double *const snl = smem + O.vli + O.snl, *const snh = smem + O.vli + O.snh, *const snu = smem + O.vli + O.snu;
@@ -110,7 +114,7 @@ __device__ __forceinline__ int sim_run_spec(const MpcLayout &L, const MpcTables 
         sm.uopt = smem + O.uopt; sm.bnd = smem + O.bnd;
         sm.z = smem + O.z; sm.lvl = smem + O.lvl; sm.w = smem + O.w; sm.wsc = smem + O.wsc;
         sm.g = smem + O.g; sm.l = smem + O.l; sm.rr = smem + O.rr; sm.mu = smem + O.mu;
-        sm.V = smem + O.vli; sm.Li = smem + O.vli + (size_t)SimWarp<NU, P, false>::QC * R;
+        sm.V = smem + O.vli; sm.Li = smem + O.vli + (size_t)SimWarp<NU, P, false, MSM>::QC * R;
         int *ip = (int *)(smem + O.ints);
         sm.chd = sm.chj = sm.role = nullptr;
         sm.act = ip; ip += R; sm.dflag = ip; ip += R; sm.misc = ip;
@@ -138,6 +142,11 @@ __device__ __forceinline__ int sim_run_spec(const MpcLayout &L, const MpcTables 
 #pragma unroll
     for (int j = 0; j < NU; ++j) wp.u[j] = 0.0;
     // ---- one-time staging ----
+    if (MSM) {
+        double *msm = smem + ((O.total + 1) & ~1);
+        for (int i = lane; i < nst * R; i += 32) msm[i] = Mg[i];
+        wp.Mp = msm;
+    } else
     wp.Mp = Mg;   // M stays in global memory (L2): read once per speculative block / per constrained sample
     sm.chg[lane] = lane < nch ? L.gain[lane] : 0.0;
     sm.x[lane] = 0.0; sm.xol[lane] = 0.0;
@@ -218,7 +227,7 @@ __device__ __forceinline__ int sim_run_spec(const MpcLayout &L, const MpcTables 
             for (int e = 0; e < SIM_SPEC_CB; ++e)
 #pragma unroll
                 for (int s = 0; s < NSLOT; ++s)
-                    mv[e][s] = (wp.valid[s] && c0 + e < nst) ? __ldg(mp + (size_t)(c0 + e) * R + s * 32) : 0.0;
+                    mv[e][s] = (wp.valid[s] && c0 + e < nst) ? (MSM ? mp[(size_t)(c0 + e) * R + s * 32] : __ldg(mp + (size_t)(c0 + e) * R + s * 32)) : 0.0;
 #pragma unroll
             for (int e = 0; e < SIM_SPEC_CB; e += 2) {
 #pragma unroll

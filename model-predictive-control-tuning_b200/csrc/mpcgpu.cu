@@ -297,7 +297,7 @@ extern "C" int mpcgpu_create(const mpcgpu_problem *problem, int device, mpcgpu_h
             if ((ce = cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin)) != cudaSuccess)
                 return fail("cudaFuncSetAttribute(closed-loop kernel)", ce);
     }
-    for (int v = 0; v < 3; ++v)
+    for (int v = 0; v < 4; ++v)
         if ((ce = cudaFuncSetAttribute(sim_spec(t.L.nu, v), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin)) != cudaSuccess)
             return fail("cudaFuncSetAttribute(k_sim spec)", ce);
     if ((ce = cudaFuncSetAttribute(soft_est_kernel(t.L.nu), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin)) != cudaSuccess)
@@ -558,6 +558,7 @@ extern "C" int mpcgpu_run(mpcgpu_handle *h, int cost_mode, int want_traj, void *
             const bool lean = cost_mode == MPCGPU_COST_GAM && !want_traj && !h->want_diag;   // the tuning loop's call
             const bool vlean = cost_mode == MPCGPU_COST_VNS && !want_traj && !h->want_diag;   // ... and its VNS phase
             size_t smem = (spec ? sim_spec_smem_doubles(L, nu, bk.P, lean) : sim_smem_doubles(L, nu, bk.P)) * sizeof(double);
+            bool msm = false;
             {   // Resident runs per SM.  The kernel is bound by instruction fetch: co-resident runs slow
                 // each other down, so a SMALL population, whose step lasts as long as its heaviest run, finishes sooner with
                 // fewer runs per SM (measured on 4096 Shell3x3 candidates: 10.4 ms at 10 per SM, 9.1 ms at 5), while a large
@@ -565,8 +566,12 @@ extern "C" int mpcgpu_run(mpcgpu_handle *h, int cost_mode, int want_traj, void *
                 static const int rps_env = getenv("MPCGPU_RUNS_PER_SM") ? atoi(getenv("MPCGPU_RUNS_PER_SM")) : 0;
                 const int rps = rps_env > 0 ? rps_env : ((long long)grid <= 40LL * h->sm_count ? 5 : 0);
                 if (rps > 0) { const size_t want = (size_t)(228 * 1024) / rps - 1024; if (want > smem && want <= h->smem_optin) smem = want; }
+                // ... and such a launch has the shared memory to spare for M itself (GAM cost-only image; MPCGPU_MSM=0: off)
+                static const bool msm_off = getenv("MPCGPU_MSM") && atoi(getenv("MPCGPU_MSM")) == 0;
+                const size_t need = (((sim_spec_smem_doubles(L, nu, bk.P, true) + 1) & ~(size_t)1) + sim_spec_msm_doubles(nu, bk.P)) * sizeof(double);
+                msm = spec && lean && rps > 0 && !msm_off && need <= smem;
             }
-            (spec ? sim_spec(nu, lean ? 1 : (vlean ? 2 : 0))
+            (spec ? sim_spec(nu, msm ? 3 : (lean ? 1 : (vlean ? 2 : 0)))
                   : (lean ? sim_lean(nu, bk.P) : (vlean ? sim_vlean(nu, bk.P) : sim_kernel(nu, bk.P))))<<<grid, 32, smem, h->pool[b % NSTREAM]>>>(L, T, h->dOrder.p + bk.off, bk.count, runs, cost_mode,
                                                                            square, item0, C, O);
             if (spec) {
