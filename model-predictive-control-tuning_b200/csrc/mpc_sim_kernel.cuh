@@ -40,7 +40,10 @@ template <int NU, int P, bool LEAN = false, bool VLEAN = false, bool SPEC = fals
 #ifndef SIM_SPEC_MINB
 #define SIM_SPEC_MINB 12   /* resident runs per SM the speculative kernel's register budget is sized for */
 #endif
-__global__ void __launch_bounds__(32, SPEC ? SIM_SPEC_MINB : 1) k_sim(const MpcLayout L, const MpcTables T, const int *order, int count, int runs,
+#ifndef SIM_MSM_MINB
+#define SIM_MSM_MINB 5     /* ... and of its small-population image (M in shared memory: at most 5 runs per SM are launched) */
+#endif
+__global__ void __launch_bounds__(32, SPEC ? (MSM ? SIM_MSM_MINB : SIM_SPEC_MINB) : 1) k_sim(const MpcLayout L, const MpcTables T, const int *order, int count, int runs,
                                             int mode, int square, long long item0, DevCand C, DevOut O) {
     extern __shared__ __align__(16) double smem_s[];
     const int item = blockIdx.x;
