@@ -587,7 +587,7 @@ def main():
             "roofline": {"bound": "fp64_fma (latency-bound serial QP chain; neither hbm nor tensor, SURVEY.md 8d)",
                          "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak if fp64_peak else None,
                          "peak_source": "mpcgpu_measure_fp64_peak, measured live (MEASURED_PEAKS.json has no fp64 entry)",
-                         "kernel": "k_build + " + ("k_soft<3,16> (block per run, soft output limits)" if (np.isfinite(prob.ymin).any() or np.isfinite(prob.ymax).any()) else "k_sim<3,16,lean,spec> (warp per run, speculative)") + ", one launch per population",
+                         "kernel": "k_build + " + ("k_soft<3,16> (block per run, soft output limits)" if (np.isfinite(prob.ymin).any() or np.isfinite(prob.ymax).any()) else "k_sim<3,16,lean,spec[,M in shared memory for small populations]> (warp per run, speculative)") + ", one launch per population",
                          "kernel_ms": {"k_sim": sim_ms, "k_build": build_ms},
                          "algorithmic_flops_per_launch": f_survey * runs,
                          "executed_flops_per_launch": flops * runs, "executed_tflops": executed,
