@@ -19,7 +19,9 @@
 #include "mpc_layout.h"
 #include "mpc_sim.cuh"
 
+#ifndef SOFT_THREADS
 #define SOFT_THREADS 128
+#endif
 #define SOFT_SYNC() __syncthreads()
 // |d2|^2 is a plain sum of squares here (no cancellation), so linear dependence is tested at the same level as the
 // reference restatement (oracle DEP_TOL); the Schur form of mpc_sim.cuh needs the coarser SIM_DEP_TOL.
@@ -102,14 +104,16 @@ struct SoftSm {
 // deterministic block reductions (fixed order: shuffle tree inside each warp, then the warps' partial results in warp order):
 // every thread returns the result.  Two block barriers each; the first version (a seven-level tree through shared memory,
 // eight barriers) was a fifth of an active-set iteration.
-static_assert(SOFT_THREADS == 128, "four warps");
+static_assert(SOFT_THREADS % 32 == 0 && SOFT_THREADS >= 32 && SOFT_THREADS <= 256, "whole warps");
 __device__ __forceinline__ double soft_sum(double v, const SoftSm &sm) {
     const int tid = threadIdx.x;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     if ((tid & 31) == 0) sm.red[tid >> 5] = v;
     SOFT_SYNC();
-    const double r = (sm.red[0] + sm.red[1]) + (sm.red[2] + sm.red[3]);
+    double r = sm.red[0];
+#pragma unroll
+    for (int w = 1; w < SOFT_THREADS / 32; ++w) r += sm.red[w];
     SOFT_SYNC();
     return r;
 }
