@@ -153,20 +153,20 @@ def other_configs():
     try:
         p7 = mpcgpu.shell7x5(); e7 = mpcgpu.Evaluator(p7, device=0)
         P7 = mpcgpu.synthetic_population(p7, 2048, seed=0)
-        e7.eval_batch(*[a[:64] for a in P7], mode="gam")
+        e7.eval_batch(*P7, mode="gam")   # warm-up at full size (device buffers are allocated on first use)
         t0 = time.perf_counter(); o7 = e7.eval_batch(*P7, mode="gam"); dt = time.perf_counter() - t0
         out["shell7x5_soft_constraints"] = {"candidates": 2048, "candidates_per_s": 2048 / dt, "failed": int((o7["status"] != 0).sum()),
                                             "weights": "lambda log-uniform [1e-4, 10] (the survey's full range), delta = 0 (band control)"}
         e7.close()
         pd = mpcgpu.woodberry_dtc(); ed = mpcgpu.DtcEvaluator(pd, device=0)
         Pd = mpcgpu.synthetic_dtc_population(pd, 16384, seed=0)
-        ed.eval_batch(*[a[:64] for a in Pd[:4]], alfa=Pd[4][:64], raio=Pd[5][:64])
+        ed.eval_batch(*Pd[:4], alfa=Pd[4], raio=Pd[5])
         t0 = time.perf_counter(); od = ed.eval_batch(*Pd[:4], alfa=Pd[4], raio=Pd[5]); dt = time.perf_counter() - t0   # robustness filters designed on the device
         out["dtc_gpc_sweep"] = {"candidates": 16384, "candidates_per_s": 16384 / dt, "failed": int((od["status"] != 0).sum())}
         ed.close()
         pn = mpcgpu.vandevusse(); en = mpcgpu.NmpcEvaluator(pn, device=0)
         Pn = mpcgpu.synthetic_nmpc_population(pn, 16384, seed=0)
-        en.eval_batch(*[a[:64] for a in Pn], mode="gam")
+        en.eval_batch(*Pn, mode="gam")
         t0 = time.perf_counter(); on = en.eval_batch(*Pn, mode="gam"); dt = time.perf_counter() - t0
         out["vandevusse_nmpc"] = {"candidates": 16384, "candidates_per_s": 16384 / dt, "failed": int((~np.isin(on["status"], (0, 5))).sum())}
         en.close()
