@@ -63,3 +63,25 @@ def test_shard_indices_partition():
     assert np.array_equal(allidx, np.arange(101))
     loads = [w[p].sum() for p in parts]
     assert max(loads) / min(loads) < 1.15     # sorted round-robin balances the estimated work
+
+
+def test_python_work_key_equals_the_library_key():
+    """Both multi-GPU front ends must deal the same shards: mpcgpu.distributed.work_estimate (torchrun path) against
+    mpcgpu_work_estimate (the key mpcgpu_create_multi and the launch order use; pure host code, callable without a GPU),
+    for a plant with hard MV limits only and for one with soft output bands."""
+    import ctypes as C
+    import mpcgpu
+    from mpcgpu import _capi
+    from mpcgpu.distributed import work_estimate
+    lib = _capi.load_library()
+    for prob, soft in ((mpcgpu.shell3x3(2), False), (mpcgpu.shell7x5(), True)):
+        ps, keep = _capi.make_problem_struct(prob)
+        N, Nu, dl, lm = mpcgpu.synthetic_population(prob, 300, seed=2)
+        N = np.ascontiguousarray(N, dtype=np.int32); Nu = np.ascontiguousarray(Nu, dtype=np.int32)
+        dl = np.ascontiguousarray(dl, dtype=np.float64); lm = np.ascontiguousarray(lm, dtype=np.float64)
+        w = np.zeros(len(N))
+        P = lambda a: a.ctypes.data_as(C.c_void_p)
+        assert lib.mpcgpu_work_estimate(C.byref(ps), len(N), P(N), P(Nu), P(dl), P(lm), P(w)) == 0
+        wp = work_estimate(N, Nu, dl, lm, dead_max=int(prob.plant.d.max()), soft=soft)
+        np.testing.assert_allclose(w, wp, rtol=1e-12, atol=1e-12)
+        assert np.array_equal(np.argsort(-w, kind="stable"), np.argsort(-wp, kind="stable"))
