@@ -118,7 +118,8 @@ __global__ void __launch_bounds__(SOFT_THREADS, SOFT_MINB) k_soft(const MpcLayou
     const long long t_start = clock64();
     const int sel = mode == 2 ? (square ? run : -1) : -2;
     const int st = soft_run<NU, P, EST>(L, T, C.N[c], C.Nu[c], C.M + C.offM[c], C.W + C.offW[c], mode, sel, smem_f, out,
-                                        EST ? C.est : nullptr, EST ? C.delta + (size_t)c * ny : nullptr);
+                                        EST ? C.est : nullptr, EST ? C.delta + (size_t)c * ny : nullptr,
+                                        C.scratch ? C.scratch + (size_t)(item0 + item) * C.scratch_stride : nullptr);
     if (st != 0 && threadIdx.x == 0) atomicMax(O.status + c, st);
     if (out.diag && threadIdx.x == 0) out.diag[3] = (unsigned long long)(clock64() - t_start);
 }

@@ -160,6 +160,8 @@ struct SoftQP {
     SoftSm sm;
     const double *W;   // global: R x R inverse Hessian (padded layout)
     int p, m, q, tid, n_rot, ne, npref;
+    double *j0g;     // per-run global scratch for J0 (NV x ne doubles) or nullptr
+    int j0_valid;
     unsigned long long n_con, n_it;
     int qmax;
 
@@ -276,6 +278,14 @@ struct SoftQP {
     // J0 = Cholesky factor of H^-1 over the live variables (W is H^-1 of the moves; the slack is decoupled)
     __device__ __forceinline__ int factor_init() {
         const int nzu = NU * m;
+        if (j0g && j0_valid) {   // J0 depends on the candidate only: computed once per run, afterwards a copy (ncu r2: the
+            // Cholesky with its runtime index maps was 20 % of the kernel's instructions once J is refreshed at every QP)
+            for (int idx = tid; idx < NV * ne; idx += SOFT_THREADS) sm.V[idx] = j0g[idx];
+            SOFT_SYNC();
+            q = 0;
+            n_rot = 0;
+            return 0;
+        }
         for (int idx = tid; idx < NV * ne; idx += SOFT_THREADS) {
             const int e2 = idx / NV, r = idx - e2 * NV;
             double v = 0.0;
@@ -300,6 +310,11 @@ struct SoftQP {
                 const int e2 = k + 1 + idx / NV, r = idx - (idx / NV) * NV;
                 if (emap(r) >= e2) sm.V[(size_t)e2 * NV + r] -= sm.V[(size_t)k * NV + r] * sm.V[(size_t)k * NV + rmap(e2)];
             }
+            SOFT_SYNC();
+        }
+        if (j0g) {
+            for (int idx = tid; idx < NV * ne; idx += SOFT_THREADS) j0g[idx] = sm.V[idx];
+            j0_valid = 1;
             SOFT_SYNC();
         }
         q = 0;
@@ -376,13 +391,20 @@ struct SoftQP {
             sm.w[t] = sqrt(ss);
         }
         SOFT_SYNC();
+        // the rotation (c_j, s_j) that folds component j into j-1 is the same for every row of J: computed once (it was two fp64
+        // divisions per row and step: 9 % of the kernel's instructions)
+        for (int t = 1 + tid; t < nt; t += SOFT_THREADS) {
+            const double sj1 = sm.w[t - 1], sj = sm.w[t];
+            double c = 1.0, s = 0.0;
+            if (sj1 > 0.0) { c = sm.g[q + t - 1] / sj1; s = sj / sj1; }
+            sm.wsc[t] = c; sm.nrm[t] = s;
+        }
+        SOFT_SYNC();
         for (int r = tid; r < NV; r += SOFT_THREADS) {
             // the carried component must be +sigma: flip the last column if its d entry is negative (J J' is unchanged)
             double carry = sm.g[ne - 1] < 0.0 ? -sm.V[(size_t)(ne - 1) * NV + r] : sm.V[(size_t)(ne - 1) * NV + r];
             for (int j = ne - 1; j > q; --j) {
-                const double sj1 = sm.w[j - 1 - q], sj = sm.w[j - q];
-                double c = 1.0, s = 0.0;
-                if (sj1 > 0.0) { c = sm.g[j - 1] / sj1; s = sj / sj1; }
+                const double c = sm.wsc[j - q], s = sm.nrm[j - q];
                 const double o = sm.V[(size_t)(j - 1) * NV + r];
                 sm.V[(size_t)j * NV + r] = c * carry - s * o;
                 carry = c * o + s * carry;
@@ -686,7 +708,7 @@ struct SoftQP {
 template <int NU, int P, bool EST = false>
 __device__ __forceinline__ int soft_run(const MpcLayout &L, const MpcTables &T, int p, int m, const double *__restrict__ Mg,
                                         const double *__restrict__ Wg, int mode, int sel, double *smem, const MpcRunOut &out,
-                                        const MpcEst *E = nullptr, const double *delta = nullptr) {
+                                        const MpcEst *E = nullptr, const double *delta = nullptr, double *j0g = nullptr) {
     constexpr int R = NU * P;
     constexpr int NV = R + 1;
     constexpr int QM = NV;
@@ -728,7 +750,7 @@ __device__ __forceinline__ int soft_run(const MpcLayout &L, const MpcTables &T, 
         for (int i = tid; i < nw * HLP; i += SOFT_THREADS) histp[i] = 0.0;
         for (int i = tid; i < ny; i += SOFT_THREADS) { xod[i] = 0.0; einn[i] = 0.0; const double w = delta[i] / L.sy[i]; wy2[i] = w * w; }
     }
-    qp.W = Wg; qp.p = p; qp.m = m; qp.q = 0; qp.tid = tid; qp.npref = 0; qp.n_rot = 0; qp.n_con = 0; qp.n_it = 0; qp.qmax = 0;
+    qp.W = Wg; qp.p = p; qp.m = m; qp.q = 0; qp.tid = tid; qp.npref = 0; qp.j0g = j0g; qp.j0_valid = 0; qp.n_rot = 0; qp.n_con = 0; qp.n_it = 0; qp.qmax = 0;
     qp.ne = NU * m + 1;
     // ---- one-time staging ----
     for (int ch = tid; ch < nch; ch += SOFT_THREADS) {

@@ -480,7 +480,8 @@ extern "C" int mpcgpu_run(mpcgpu_handle *h, int cost_mode, int want_traj, void *
     // spill area: only rows beyond QC (= 16 active constraints) of the P = 16 bucket ever touch it
     long long scr_stride = 0, scr_items = 0;
     for (const auto &bk : h->buckets) {
-        const long long sd = (long long)sim_scratch_doubles(nu * bk.P);
+        // hard-limit kernels: spill area of the active-set factor; block-per-run kernel (soft bands / validation run): J0 of the run
+        const long long sd = (L.has_ov_bounds || h->dEst) ? (long long)(nu * bk.P + 1) * (nu * bk.P + 1) : (long long)sim_scratch_doubles(nu * bk.P);
         if (sd > scr_stride) scr_stride = sd;
         scr_items += (long long)bk.count * runs;
     }
