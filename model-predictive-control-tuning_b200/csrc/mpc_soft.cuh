@@ -49,6 +49,9 @@
 #define SOFT_POLISH 1   /* at exit recompute the optimum from the final active set alone, z = z_unc + J1 R^-T (b_A - N_A' z_unc), instead of
                            keeping the sum of the steps that led there: the result then depends on the set, not on the path */
 #endif
+#ifndef SOFT_TCH
+#define SOFT_TCH 8   /* prediction steps per thread in the evaluation of y = yfree + G z (SOFT_THREADS / ny threads x SOFT_TCH >= pmax) */
+#endif
 #ifndef SOFT_REFRESH_ROT
 #define SOFT_REFRESH_ROT 0   /* rotations after which J is rebuilt from H^-1 (cold-start mode).  0 = at every constrained QP: J drifts
                                under the Givens rotations (cond(H) reaches 1e12 here), and a drifting J made the result depend on
@@ -502,32 +505,39 @@ struct SoftQP {
     __device__ __forceinline__ void evaluate(bool with_outputs) const {
         scan(sm.z, sm.lvl, sm.ucur);
         if (with_outputs) {
-            // y = yfree + G z for every prediction row.  A thread owns output i and a chunk of consecutive prediction steps and
-            // slides a P-wide window of the step response along it: one table load per row and input instead of one per
-            // multiply-add (ncu r2: the row-by-row form, ov_dot, was 19 % of the kernel's instructions).  Same products in the same
-            // order as ov_dot -- the window holds zeros where ov_dot's loop ends (c >= min(t, m)) -- so the sums are bit-identical.
-            const int ny = L.ny, nchunk = SOFT_THREADS / ny, tch = (p + nchunk - 1) / nchunk;
-            const int i = tid % ny, t0 = 1 + (tid / ny) * tch, t1 = t0 + tch - 1 < p ? t0 + tch - 1 : p;
-            if (tid < ny * nchunk && t0 <= t1) {
+            // y = yfree + G z for every prediction row.  A thread owns output i and SOFT_TCH consecutive prediction steps
+            // t0 .. t0+TCH-1; every step-response value s(n) it needs is loaded ONCE and feeds all the rows it belongs to
+            // (row t takes s(t - c) x_c): TCH + P - 1 table loads and TCH x P multiply-adds per input with every index a
+            // compile-time constant (ncu r2: the row-by-row form, ov_dot, was 19 % of the kernel's instructions, one load per
+            // multiply-add).  The values are visited in descending n, i.e. ascending c for every row, and zeros stand where
+            // ov_dot's loop ends (c >= min(t, m)): the same products in the same order, bit-identical sums.
+            constexpr int TCH = SOFT_TCH;
+            const int ny = L.ny;
+            const int i = tid % ny, t0 = 1 + (tid / ny) * TCH;
+            if (tid < ny * (SOFT_THREADS / ny) && t0 <= p) {
+                double acc[TCH];
 #pragma unroll 1
                 for (int j = 0; j < NU; ++j) {
                     const double *s = T.ST + (size_t)(i * NU + j) * T.st_stride;
-                    double xr[P], w[P];
+                    double xr[P], a[TCH];
 #pragma unroll
-                    for (int c = 0; c < P; ++c) { xr[c] = c < m ? sm.z[j * P + c] : 0.0; w[c] = t0 - c >= 1 ? __ldg(s + (t0 - c)) : 0.0; }
-#pragma unroll 1
-                    for (int t = t0; t <= t1; ++t) {
-                        double a = 0.0;
+                    for (int c = 0; c < P; ++c) xr[c] = c < m ? sm.z[j * P + c] : 0.0;
 #pragma unroll
-                        for (int c = 0; c < P; ++c) a = fma(w[c], xr[c], a);
-                        const int row = (t - 1) * ny + i;
-                        sm.ypred[row] = j == 0 ? a : sm.ypred[row] + a;
+                    for (int k = 0; k < TCH; ++k) a[k] = 0.0;
 #pragma unroll
-                        for (int c = P - 1; c > 0; --c) w[c] = w[c - 1];
-                        w[0] = __ldg(s + (t + 1));
+                    for (int c0 = -(TCH - 1); c0 < P; ++c0) {            // n = t0 - c0 descends as c0 rises
+                        const int n = t0 - c0;
+                        const double sv = n >= 1 ? __ldg(s + n) : 0.0;
+#pragma unroll
+                        for (int k = 0; k < TCH; ++k)
+                            if (k + c0 >= 0 && k + c0 < P) a[k] = fma(sv, xr[k + c0], a[k]);   // row t0 + k, move c = k + c0
                     }
+#pragma unroll
+                    for (int k = 0; k < TCH; ++k) acc[k] = j == 0 ? a[k] : acc[k] + a[k];
                 }
-                for (int t = t0; t <= t1; ++t) { const int row = (t - 1) * ny + i; sm.ypred[row] = sm.yfree[row] + sm.ypred[row]; }
+#pragma unroll
+                for (int k = 0; k < TCH; ++k)
+                    if (t0 + k <= p) { const int row = (t0 + k - 1) * ny + i; sm.ypred[row] = sm.yfree[row] + acc[k]; }
             }
         }
         SOFT_SYNC();

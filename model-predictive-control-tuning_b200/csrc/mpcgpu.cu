@@ -313,7 +313,7 @@ extern "C" int mpcgpu_create(const mpcgpu_problem *problem, int device, mpcgpu_h
     }
     if (t.L.has_ov_bounds) {   // soft output constraints run on the block-per-run kernel (mpc_soft.cuh)
         const size_t sf = soft_smem_doubles(t.L, t.L.nu, sim_pad(t.L.mmax)) * sizeof(double);
-        if (sf > h->smem_optin || t.L.nst > SOFT_THREADS || !(t.L.rho_ecr > 0.0)) {
+        if (sf > h->smem_optin || t.L.nst > SOFT_THREADS || !(t.L.rho_ecr > 0.0) || (SOFT_THREADS / t.L.ny) * SOFT_TCH < t.L.pmax) {
             g_create_error = "soft output constraints: problem too large for the block kernel (shared memory " +
                              std::to_string(sf) + " B, nst " + std::to_string(t.L.nst) + ") or Weights.ECR <= 0";
             mpcgpu_destroy(h);
@@ -700,6 +700,7 @@ extern "C" int mpcgpu_set_mismatch(mpcgpu_handle *h, const double *plant_a, cons
     const MpcLayout &L = h->ht.L;
     if (!plant_b0 || !plant_b1 || !plant_d || !gain || hl < 1) { h->err = "mpcgpu_set_mismatch: NULL argument / hl < 1"; return MPCGPU_ERR_ARG; }
     const int nch = L.ny * L.nw;
+    if (L.nst > SOFT_THREADS || (SOFT_THREADS / L.ny) * SOFT_TCH < L.pmax) { h->err = "mpcgpu_set_mismatch: problem too large for the block-per-run kernel"; return MPCGPU_ERR_UNSUPPORTED; }
     MpcEst e;
     memset(&e, 0, sizeof(e));
     int dmax = 0;
