@@ -57,3 +57,16 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", "Makefile")):
                 src = open(os.path.join(dp, f)).read()
                 assert not pat.search(src), f
+
+
+def test_header_is_plain_c(tmp_path):
+    """The boundary is a C ABI: include/mpcgpu.h must compile as C99 (and as C++) on its own, with no CUDA or torch types."""
+    import subprocess
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "mpcgpu.h"\nint main(void) { return sizeof(mpcgpu_problem) + sizeof(mpcgpu_nmpc_problem) + sizeof(mpcgpu_dtc_problem) > 0 ? 0 : 1; }\n')
+    inc = os.path.join(ROOT, "include")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", inc, "-fsyntax-only", str(src)])
+    subprocess.check_call(["g++", "-std=c++11", "-Wall", "-Werror", "-I", inc, "-fsyntax-only", "-x", "c++", str(src)])
+    hdr = open(os.path.join(inc, "mpcgpu.h")).read()
+    assert "cudaStream_t" not in hdr and "#include <cuda" not in hdr      # streams cross the boundary as void *
+    assert "torch" not in hdr and "at::" not in hdr
