@@ -38,3 +38,19 @@ def eval_batch(prob, N, Nu, delta, lam, mode="gam", traj=False, r=None, v=None, 
     if rc:
         raise RuntimeError(err.value.decode())
     return cost, status, counters, tr
+
+
+def eval_est(prob, plant, gain, hl, N, Nu, delta, lam):
+    """Host emulation of the validation run against a mismatched plant (k_soft<NU,16,true>), one candidate: y, u, cost, status."""
+    ps, keep = make_problem_struct(prob)
+    a, b0, b1 = (np.ascontiguousarray(x, dtype=np.float64) for x in (plant.a, plant.b0, plant.b1))
+    d = np.ascontiguousarray(plant.d, dtype=np.int32)
+    g = np.ascontiguousarray(gain, dtype=np.float64)
+    dl = np.ascontiguousarray(delta, dtype=np.float64); lm = np.ascontiguousarray(lam, dtype=np.float64)
+    y = np.zeros((prob.ny, ps.nit)); u = np.zeros((prob.nu, ps.nit)); cost = np.zeros(prob.ny)
+    P = lambda x: x.ctypes.data_as(C.c_void_p)
+    err = C.create_string_buffer(256)
+    rc = lib().emu_eval_est(C.byref(ps), P(a), P(b0), P(b1), P(d), P(g), int(hl), int(N), int(Nu), P(dl), P(lm), P(cost), P(y), P(u), err, 256)
+    if rc < 0:
+        raise RuntimeError(err.value.decode())
+    return y, u, cost, rc

@@ -66,25 +66,27 @@ static int sim_dispatch(int nu, int P, const MpcLayout &L, const MpcTables &T, i
 
 template <int NU>
 static int soft_p(int P, const MpcLayout &L, const MpcTables &T, int p, int m, const double *Mg, const double *Wg, int mode, int sel,
-                  double *smem, const MpcRunOut &out) {
+                  double *smem, const MpcRunOut &out, double *j0g, const MpcEst *E = nullptr, const double *delta = nullptr) {
+    if (E) return soft_run<NU, 16, true>(L, T, p, m, Mg, Wg, mode, sel, smem, out, E, delta, j0g);   // validation run: P = 16 image only
     switch (P) {
-        case 4: return soft_run<NU, 4>(L, T, p, m, Mg, Wg, mode, sel, smem, out);
-        case 8: return soft_run<NU, 8>(L, T, p, m, Mg, Wg, mode, sel, smem, out);
-        default: return soft_run<NU, 16>(L, T, p, m, Mg, Wg, mode, sel, smem, out);
+        case 4: return soft_run<NU, 4>(L, T, p, m, Mg, Wg, mode, sel, smem, out, nullptr, nullptr, j0g);
+        case 8: return soft_run<NU, 8>(L, T, p, m, Mg, Wg, mode, sel, smem, out, nullptr, nullptr, j0g);
+        default: return soft_run<NU, 16>(L, T, p, m, Mg, Wg, mode, sel, smem, out, nullptr, nullptr, j0g);
     }
 }
 // one CTA = SOFT_THREADS host threads (plants with soft output constraints)
 static int run_block(int nu, int P, const MpcLayout &L, const MpcTables &T, int p, int m, const double *Mg, const double *Wg,
-                     int mode, int sel, const MpcRunOut &out) {
-    std::vector<double> smem(soft_smem_doubles(L, nu, P) + 8, std::nan(""));
+                     int mode, int sel, const MpcRunOut &out, const MpcEst *E = nullptr, const double *delta = nullptr) {
+    std::vector<double> smem(soft_smem_doubles(L, nu, P) + (E ? soft_est_doubles(L, nu, P, E->hlp) : 0) + 8, std::nan(""));
+    std::vector<double> j0((size_t)(nu * P + 1) * (nu * P + 1), std::nan(""));   // the run's J0 scratch (global memory on the device)
     int status[SOFT_THREADS];
     simt_run_block([&]() {
         int st;
         switch (nu) {
-            case 1: st = soft_p<1>(P, L, T, p, m, Mg, Wg, mode, sel, smem.data(), out); break;
-            case 2: st = soft_p<2>(P, L, T, p, m, Mg, Wg, mode, sel, smem.data(), out); break;
-            case 3: st = soft_p<3>(P, L, T, p, m, Mg, Wg, mode, sel, smem.data(), out); break;
-            default: st = soft_p<4>(P, L, T, p, m, Mg, Wg, mode, sel, smem.data(), out); break;
+            case 1: st = soft_p<1>(P, L, T, p, m, Mg, Wg, mode, sel, smem.data(), out, j0.data(), E, delta); break;
+            case 2: st = soft_p<2>(P, L, T, p, m, Mg, Wg, mode, sel, smem.data(), out, j0.data(), E, delta); break;
+            case 3: st = soft_p<3>(P, L, T, p, m, Mg, Wg, mode, sel, smem.data(), out, j0.data(), E, delta); break;
+            default: st = soft_p<4>(P, L, T, p, m, Mg, Wg, mode, sel, smem.data(), out, j0.data(), E, delta); break;
         }
         status[threadIdx.x] = st;
     }, SOFT_THREADS);
@@ -164,6 +166,33 @@ extern "C" int emu_eval_batch(const mpcgpu_problem *pb, int n, const int *N, con
         if (status) status[c] = st;
     }
     return 0;
+}
+
+// Validation run against a mismatched plant (mpcgpu_set_mismatch / k_soft<NU,16,true>) for ONE candidate: the real plant's
+// channels (ny x nw row-major), the estimator gain and hl as in include/mpcgpu.h.  y: ny x nit, u: nu x nit, cost: ny (GAM).
+extern "C" int emu_eval_est(const mpcgpu_problem *pb, const double *pa, const double *pb0, const double *pb1, const int *pd,
+                            const double *gain, int hl, int N, int Nu, const double *delta, const double *lambda, double *cost,
+                            double *y, double *u, char *err, int errlen) {
+    MpcHostTables ht;
+    std::string e = mpc_build_tables(*pb, ht);
+    if (!e.empty()) { std::strncpy(err, e.c_str(), errlen - 1); return -1; }
+    const MpcLayout &L = ht.L;
+    MpcTables T{ht.TG.data(), ht.TK.data(), ht.S1.data(), ht.r.data(), ht.v.data(), ht.yref.data(),
+                ht.step.data(), ht.pa.data(), L.pmax + L.mmax + 2, ht.sig.data()};
+    const int nu = L.nu, P = 16, R = nu * P, nz = nu * Nu, nch = L.ny * L.nw;
+    MpcEst E;
+    std::memset(&E, 0, sizeof(E));
+    int dmax = 0;
+    for (int c = 0; c < nch; ++c) { E.a[c] = pa[c]; E.b0[c] = pb0[c]; E.b1[c] = pb1[c]; E.d[c] = pd[c]; dmax = std::max(dmax, pd[c]); }
+    E.hl = hl; E.hlp = dmax + 2; E.gain = gain;
+    std::vector<double> bsm(mpc_builder_smem_doubles(nz, L.nst));
+    std::vector<double> Mg((size_t)L.nst * R), Wg((size_t)2 * R * R);
+    int flag = 0;
+    int st = mpc_build_candidate(L, T, N, Nu, P, delta, lambda, bsm.data(), Mg.data(), Wg.data(), &flag);
+    if (st) return st;
+    unsigned long long counters[2] = {0, 0};
+    MpcRunOut out{cost, y, u, nullptr, nullptr, counters, nullptr, nullptr};
+    return run_block(nu, P, L, T, N, Nu, Mg.data(), Wg.data(), 1, -2, out, &E, delta);
 }
 
 // shared-memory footprint of one closed-loop run (bytes) for padded control horizon P: occupancy bookkeeping

@@ -104,3 +104,26 @@ def test_two_phase_limit_cycle_reentry():
         emu.lib().emu_set_knob(0)
     assert np.allclose(g1, g2, rtol=1e-9)
     assert int(cnt2[1]) > 400 and int(cnt[1]) < int(cnt2[1]) // 3, (cnt, cnt2)
+
+
+def test_validation_run_against_a_mismatched_plant():
+    """The validation image of the block-per-run kernel (soft_run<NU,16,true>: real plant + state estimator, mpcgpu_set_mismatch)
+    executed on the host against the oracle's estimator loop, on Wood-Berry with gain and dead-time errors (WoodBerry.m:33-47).
+    With the nominal plant the run must reproduce the ordinary closed loop (zero innovation)."""
+    from mpcgpu import estimator as est
+    p = short(woodberry(), 120)
+    op = orc.OracleProblem(p)
+    plant = est.woodberry_real_plant()
+    hl = est.history_length(p, plant)
+    M = est.default_estimator_gain(p, hl)
+    cand = (14, 3, np.array([0.5, 0.5]), np.array([0.3, 0.3]))
+    y0, u0, _, _, rc0, _ = orc.closedloop(op, *cand, open_loop=False)
+    ya, ua, ca, rca = emu.eval_est(p, p.plant, M, hl, *cand)
+    assert rc0 == 0 and rca == 0
+    assert np.abs(ya - y0).max() < 1e-9 and np.abs(ua - u0).max() < 1e-9
+    y1, u1, rc1, _ = orc.closedloop_est(op, plant, M, *cand)
+    yb, ub, cb, rcb = emu.eval_est(p, plant, M, hl, *cand)
+    assert rc1 == 0 and rcb == 0
+    assert np.abs(yb - y1).max() < TOL_TRAJ and np.abs(ub - u1).max() < TOL_TRAJ, (np.abs(yb - y1).max(), np.abs(ub - u1).max())
+    np.testing.assert_allclose(cb, ((y1 - op.yref) ** 2).sum(axis=1), rtol=1e-6)
+    assert np.abs(y1 - y0).max() > 1e-3
