@@ -22,23 +22,13 @@
 
 #include "../../include/mpcgpu.h"
 
-#include "mpc_nmpc_core.h"
+#include "mpc_nmpc_group.cuh"   /* NmpcArgs, k_nmpc_g */
 #ifdef NM_GLOBAL_WORK
 #define NM_WORK_ALWAYS 1
 #else
 #define NM_WORK_ALWAYS 0
 #endif
 
-struct NmpcArgs {
-    const int *N, *Nu;
-    const double *delta, *lambda;
-    const double *r, *yref;      // ny x nit
-    double *cost, *part;         // GAM: n x ny; VNS partial: n x runs
-    double *y, *u, *yopt, *uopt; // optional n x 2 x nit
-    int *status;
-    unsigned long long *counters;   // [0] controller calls, [1] SQP iterations
-    double *work;                // per run: 2 * nz_max^2 doubles
-};
 
 // mode 0 RAW, 1 GAM, 2 VNS.  One thread per (candidate, run).  `order`: candidates sorted by (Nu, N) on the host so that
 // the 32 runs of a warp share their loop bounds (the population mixes horizons 2..31 x 1..15: unsorted, 5 of 32 lanes were
@@ -73,8 +63,6 @@ __global__ void __launch_bounds__(NM_THREADS) k_nmpc(const NmpcDev D, int n, int
     atomicAdd(A.counters + 1, (unsigned long long)n_sqp);
 }
 
-
-#include "mpc_nmpc_group.cuh"
 
 __global__ void k_nmpc_finish(int n, int runs, const int *N, const double *part, const int *status, double *cost) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;

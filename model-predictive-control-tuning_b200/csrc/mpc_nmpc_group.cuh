@@ -23,6 +23,17 @@
 #pragma once
 #include "mpc_nmpc_core.h"
 
+struct NmpcArgs {
+    const int *N, *Nu;
+    const double *delta, *lambda;
+    const double *r, *yref;      // ny x nit
+    double *cost, *part;         // GAM: n x ny; VNS partial: n x runs
+    double *y, *u, *yopt, *uopt; // optional n x 2 x nit
+    int *status;
+    unsigned long long *counters;   // [0] controller calls, [1] SQP iterations
+    double *work;                // thread-per-run kernel with NM_GLOBAL_WORK only: per run 2 * nz_max^2 doubles
+};
+
 // per-run shared memory (doubles) for plans of up to maxz variables: H, Lc packed lower triangles; v, vo, g, d, t, S0, S1
 // (maxz each); AB (16); ints fixed, fl, finv.  The host launches the population in bins of the control horizon, each with
 // the shared memory its largest plan needs: residency is bound by shared memory (9.6 KB per run at maxz = 30).
@@ -175,6 +186,8 @@ __device__ __noinline__ double nmg_model(const NmpcDev &D, const double *x0, con
         }
         // (the next sample's barrier inside nmg_rk4_sens orders these reads of S0 / S1 before the next writes)
     }
+    gp.sync();   // the last sample's accumulation into H is dealt by entry, the terms below by variable: other lanes' entries
+                 // (found by the host emulation, where lanes are threads; a converged warp hides the race, it does not remove it)
     // move-suppression terms: rows of D'Wdu^2 D
 #pragma unroll
     for (int k = 0; k < NC; ++k) {
@@ -382,11 +395,12 @@ __device__ __noinline__ int nmg_nlmpcmove(const NmpcDev &D, const double *x0, co
 
 // mode 0 RAW, 1 GAM, 2 VNS.  One group of G lanes per (candidate, run); 32 / G runs per warp, one warp per CTA.  maxz: the
 // largest plan (2 Nu) among the items of this launch.
+// (the body is a device function so that tests/host_emulation can run this source on a CPU, one warp of host threads per CTA)
 template <int G>
-__global__ void __launch_bounds__(32, NMG_MINB) k_nmpc_g(const NmpcDev D, int item0, int item1, int runs, int mode, const int *order, NmpcArgs A, int maxz) {
-    extern __shared__ double smem_g[];
+__device__ __forceinline__ void nmg_run(const NmpcDev &D, int item0, int item1, int runs, int mode, const int *order, const NmpcArgs &A,
+                                        int maxz, double *smem_g, int block) {
     const int lane = threadIdx.x & 31, grp = lane / G;
-    const int item = item0 + blockIdx.x * (32 / G) + grp;   // items [item0, item1) of the sorted order: one bin of the population
+    const int item = item0 + block * (32 / G) + grp;   // items [item0, item1) of the sorted order
     if (item >= item1) return;
     NmGroup<G> gp;
     gp.gl = lane % G;
@@ -485,3 +499,11 @@ __global__ void __launch_bounds__(32, NMG_MINB) k_nmpc_g(const NmpcDev D, int it
         atomicAdd(A.counters + 1, (unsigned long long)n_sqp);
     }
 }
+
+#ifndef MPC_SIMT_EMULATION
+template <int G>
+__global__ void __launch_bounds__(32, NMG_MINB) k_nmpc_g(const NmpcDev D, int item0, int item1, int runs, int mode, const int *order, NmpcArgs A, int maxz) {
+    extern __shared__ double smem_g[];
+    nmg_run<G>(D, item0, item1, runs, mode, order, A, maxz, smem_g, (int)blockIdx.x);
+}
+#endif

@@ -54,3 +54,20 @@ def eval_est(prob, plant, gain, hl, N, Nu, delta, lam):
     if rc < 0:
         raise RuntimeError(err.value.decode())
     return y, u, cost, rc
+
+
+def nmpc_eval(prob, N, Nu, delta, lam, mode="gam", traj=False):
+    """Host emulation of the NMPC group kernel (nmg_run<32>), one candidate: cost, status, (y, u), counters."""
+    f64 = lambda x: np.ascontiguousarray(np.asarray(x, dtype=np.float64))
+    bufs = [f64(getattr(prob, k)) for k in ("x0", "u0", "umin", "umax", "xmin", "xmax", "su", "sy", "r", "yref")]
+    dl = f64(delta); lm = f64(lam)
+    m = {"raw": 0, "gam": 1, "vns": 2}[mode]
+    cost = np.zeros(2 if m == 1 else 1)
+    y = np.zeros((2, prob.nit)) if traj else None
+    u = np.zeros((2, prob.nit)) if traj else None
+    cnt = np.zeros(2, dtype=np.uint64)
+    P = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None else None
+    st = lib().emu_nmpc_eval(C.c_int(int(prob.nit)), C.c_int(2 ** prob.nbp - 1), C.c_int(2 ** prob.nbc - 1), C.c_int(int(prob.inK)),
+                             C.c_int(int(prob.nsub)), C.c_int(int(prob.max_sqp)), C.c_double(float(prob.Ts)), *[P(b) for b in bufs],
+                             C.c_int(int(N)), C.c_int(int(Nu)), P(dl), P(lm), C.c_int(m), P(cost), P(y), P(u), P(cnt))
+    return cost, st, (y, u), cnt

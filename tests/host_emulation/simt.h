@@ -15,6 +15,7 @@
 #define __device__
 #define __host__
 #define __forceinline__ inline
+#define __noinline__
 #define __restrict__
 #define MPC_SIMT_EMULATION 1
 
@@ -114,6 +115,11 @@ static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long 
     return __atomic_fetch_add(p, v, __ATOMIC_RELAXED);
 }
 static inline double __ldg(const double *p) { return *p; }
+static inline int atomicMax(int *p, int v) {
+    int old = __atomic_load_n(p, __ATOMIC_RELAXED);
+    while (old < v && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+    return old;
+}
 
 // run fn() as one warp of 32 lanes
 static inline void simt_run_warp(const std::function<void()> &fn, unsigned block = 0) {

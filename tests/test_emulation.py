@@ -127,3 +127,28 @@ def test_validation_run_against_a_mismatched_plant():
     assert np.abs(yb - y1).max() < TOL_TRAJ and np.abs(ub - u1).max() < TOL_TRAJ, (np.abs(yb - y1).max(), np.abs(ub - u1).max())
     np.testing.assert_allclose(cb, ((y1 - op.yref) ** 2).sum(axis=1), rtol=1e-6)
     assert np.abs(y1 - y0).max() > 1e-3
+
+
+def test_nmpc_group_kernel_source_on_the_host():
+    """csrc/mpc_nmpc_group.cuh (the NMPC kernel: group-wide sensitivities, packed Hessian, cooperative box-QP, model-based
+    full-step test) executed by a warp of host threads (G = 32) against the CPU port of the same restated algorithm
+    (oracle/nmpc_port.cpp, built from mpc_nmpc_core.h: two rollouts per SQP iteration, sequential line search) and against the
+    committed output of the scipy oracle.  Same iterates, so the costs agree to rounding."""
+    import os
+    from mpcgpu.nmpc import vandevusse
+    from oracle import nmpc_port
+    p = vandevusse()
+    for cand in ((6, 2, [1.0, 1.0], [0.1, 0.1]), (10, 3, [0.5, 2.0], [0.05, 0.3])):
+        c, st, _, cnt = emu.nmpc_eval(p, *cand, mode="gam")
+        c0, s0 = nmpc_port.eval_batch(p, [cand[0]], [cand[1]], [cand[2]], [cand[3]], "gam", 1)
+        assert st == 0 and s0[0] == 0 and int(cnt[0]) == p.nit - 1 and int(cnt[1]) >= p.nit - 1
+        np.testing.assert_allclose(c, c0[0], rtol=1e-9)
+    f, st, _, _ = emu.nmpc_eval(p, 6, 2, [1.0, 1.0], [0.1, 0.1], mode="vns")
+    f0, _ = nmpc_port.eval_batch(p, [6], [2], [[1.0, 1.0]], [[0.1, 0.1]], "vns", 1)
+    np.testing.assert_allclose(f, f0, rtol=1e-6)      # (the Jnu term amplifies the last digits of the open-loop plan)
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "oracle_golden_nmpc.npz"))
+    k = int(np.argmin(gold["N"] * gold["Nu"]))
+    c, st, (y, u), _ = emu.nmpc_eval(p, int(gold["N"][k]), int(gold["Nu"][k]), gold["delta"][k], gold["lam"][k], mode="gam", traj=True)
+    assert st == 0
+    assert (np.abs(c - gold["gam"][k]) / np.abs(gold["gam"][k])).max() < 1e-5
+    assert (np.abs(y - gold["y"][k]) / p.sy[:, None]).max() < 1e-5 and (np.abs(u - gold["u"][k]) / p.su[:, None]).max() < 1e-5
