@@ -71,3 +71,18 @@ def nmpc_eval(prob, N, Nu, delta, lam, mode="gam", traj=False):
                              C.c_int(int(prob.nsub)), C.c_int(int(prob.max_sqp)), C.c_double(float(prob.Ts)), *[P(b) for b in bufs],
                              C.c_int(int(N)), C.c_int(int(Nu)), P(dl), P(lm), C.c_int(m), P(cost), P(y), P(u), P(cnt))
     return cost, st, (y, u), cnt
+
+
+def nmpc_eval_group(prob, N, Nu, delta, lam, G=16):
+    """Host emulation of the NMPC group kernel with G lanes per run: a population of candidates, 32 / G runs per warp (the
+    groups of a warp diverge where their horizons and iteration counts differ).  GAM costs and status."""
+    f64 = lambda x: np.ascontiguousarray(np.asarray(x, dtype=np.float64))
+    bufs = [f64(getattr(prob, k)) for k in ("x0", "u0", "umin", "umax", "xmin", "xmax", "su", "sy", "r", "yref")]
+    N = np.ascontiguousarray(N, dtype=np.int32); Nu = np.ascontiguousarray(Nu, dtype=np.int32); n = len(N)
+    dl = f64(delta).reshape(n, 2); lm = f64(lam).reshape(n, 2)
+    cost = np.zeros((n, 2)); status = np.zeros(n, dtype=np.int32)
+    P = lambda a: a.ctypes.data_as(C.c_void_p)
+    lib().emu_nmpc_eval_group(C.c_int(int(G)), C.c_int(int(prob.nit)), C.c_int(2 ** prob.nbp - 1), C.c_int(2 ** prob.nbc - 1), C.c_int(int(prob.inK)),
+                              C.c_int(int(prob.nsub)), C.c_int(int(prob.max_sqp)), C.c_double(float(prob.Ts)), *[P(b) for b in bufs],
+                              C.c_int(n), P(N), P(Nu), P(dl), P(lm), P(cost), P(status))
+    return cost, status

@@ -9,6 +9,9 @@
 #include <cstdint>
 #include <cstring>
 #include <functional>
+#include <map>
+#include <memory>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -26,6 +29,16 @@ struct SimtWarp {
     double xd[32];
     long long xi[32];
     unsigned vote[32];
+    // sub-warp groups (mpc_nmpc_group.cuh): a barrier per lane mask, created on first use, so that the groups of a warp may diverge
+    std::mutex mu;
+    std::map<unsigned, std::unique_ptr<std::barrier<>>> group_bars;
+    std::barrier<> &bar_of(unsigned mask) {
+        if (mask == 0xffffffffu) return bar;
+        std::lock_guard<std::mutex> lock(mu);
+        auto &b = group_bars[mask];
+        if (!b) b = std::make_unique<std::barrier<>>((std::ptrdiff_t)__builtin_popcount(mask));
+        return *b;
+    }
 };
 static thread_local SimtDim3 threadIdx, blockIdx, blockDim;
 static thread_local SimtWarp *simt_warp = nullptr;
@@ -33,32 +46,33 @@ static thread_local std::barrier<> *simt_block = nullptr;
 static inline void __syncthreads() { simt_block->arrive_and_wait(); }
 static inline long long clock64() { return 0; }
 
-static inline void __syncwarp(unsigned = 0xffffffffu) { simt_warp->bar.arrive_and_wait(); }
+static inline void __syncwarp(unsigned mask = 0xffffffffu) { simt_warp->bar_of(mask).arrive_and_wait(); }
 
 template <typename T>
-static inline T simt_xchg(T v, int src) {
+static inline T simt_xchg(T v, int src, unsigned mask = 0xffffffffu) {
     static_assert(sizeof(T) <= 8, "");
     long long raw = 0;
     std::memcpy(&raw, &v, sizeof(T));
+    std::barrier<> &b = simt_warp->bar_of(mask);
     simt_warp->xi[threadIdx.x & 31] = raw;
-    simt_warp->bar.arrive_and_wait();
+    b.arrive_and_wait();
     long long got = simt_warp->xi[src & 31];
-    simt_warp->bar.arrive_and_wait();
+    b.arrive_and_wait();
     T out;
     std::memcpy(&out, &got, sizeof(T));
     return out;
 }
 template <typename T>
-static inline T __shfl_sync(unsigned, T v, int src, int width = 32) {
+static inline T __shfl_sync(unsigned mask, T v, int src, int width = 32) {
     const int lane = threadIdx.x & 31;
     const int base = lane & ~(width - 1);
-    return simt_xchg(v, base + (src & (width - 1)));
+    return simt_xchg(v, base + (src & (width - 1)), mask);
 }
 template <typename T>
-static inline T __shfl_xor_sync(unsigned, T v, int mask, int width = 32) {
+static inline T __shfl_xor_sync(unsigned member_mask, T v, int mask, int width = 32) {
     const int lane = threadIdx.x & 31;
     (void)width;
-    return simt_xchg(v, lane ^ mask);
+    return simt_xchg(v, lane ^ mask, member_mask);
 }
 template <typename T>
 static inline T __shfl_up_sync(unsigned, T v, unsigned delta, int width = 32) {
@@ -75,12 +89,13 @@ static inline int __any_sync(unsigned, int pred) {
     simt_warp->bar.arrive_and_wait();
     return r;
 }
-static inline unsigned __ballot_sync(unsigned, int pred) {
+static inline unsigned __ballot_sync(unsigned mask, int pred) {
+    std::barrier<> &b = simt_warp->bar_of(mask);
     simt_warp->vote[threadIdx.x & 31] = pred ? 1u : 0u;
-    simt_warp->bar.arrive_and_wait();
+    b.arrive_and_wait();
     unsigned r = 0;
-    for (int i = 0; i < 32; ++i) r |= simt_warp->vote[i] << i;
-    simt_warp->bar.arrive_and_wait();
+    for (int i = 0; i < 32; ++i) if ((mask >> i) & 1u) r |= simt_warp->vote[i] << i;
+    b.arrive_and_wait();
     return r;
 }
 static inline unsigned __reduce_min_sync(unsigned, unsigned v) {

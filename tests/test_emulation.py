@@ -152,3 +152,24 @@ def test_nmpc_group_kernel_source_on_the_host():
     assert st == 0
     assert (np.abs(c - gold["gam"][k]) / np.abs(gold["gam"][k])).max() < 1e-5
     assert (np.abs(y - gold["y"][k]) / p.sy[:, None]).max() < 1e-5 and (np.abs(u - gold["u"][k]) / p.su[:, None]).max() < 1e-5
+
+
+@pytest.mark.parametrize("G", [8, 16])
+def test_nmpc_groups_of_a_warp_may_diverge(G):
+    """Several closed-loop runs share a warp in the product (G = 16: two, G = 8: four): different horizons and SQP iteration
+    counts make the groups diverge, every exchange is group-wide (__shfl_sync / __syncwarp with the group's mask).  The host
+    emulation gives every lane mask its own barrier, so a missing or mis-masked barrier shows as a deadlock or a wrong
+    result here.  Same costs as one run per warp and as the CPU port."""
+    from mpcgpu.nmpc import vandevusse
+    from oracle import nmpc_port
+    import os
+    p = vandevusse()
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "oracle_golden_nmpc.npz"))
+    N, Nu, dl, lm = gold["N"][:4], gold["Nu"][:4], gold["delta"][:4], gold["lam"][:4]      # horizons 3..10, Nu 2..4 in one warp
+    c, st = emu.nmpc_eval_group(p, N, Nu, dl, lm, G=G)
+    c1, st1 = emu.nmpc_eval_group(p, N, Nu, dl, lm, G=32)
+    c0, s0 = nmpc_port.eval_batch(p, N, Nu, dl, lm, "gam", 1)
+    assert (st == 0).all() and (st1 == 0).all() and (s0 == 0).all()
+    assert np.array_equal(c, c1)                                            # the group width does not change the arithmetic
+    assert (np.abs(c - c0) / np.abs(c0)).max() < 1e-6
+    assert (np.abs(c - gold["gam"][:4]) / np.abs(gold["gam"][:4])).max() < 1e-5
