@@ -86,3 +86,32 @@ def nmpc_eval_group(prob, N, Nu, delta, lam, G=16):
                               C.c_int(int(prob.nsub)), C.c_int(int(prob.max_sqp)), C.c_double(float(prob.Ts)), *[P(b) for b in bufs],
                               C.c_int(n), P(N), P(Nu), P(dl), P(lm), P(cost), P(status))
     return cost, status
+
+
+def dtc_eval(prob, p, m, delta, lam, alfa, raio, traj=True):
+    """Host emulation of the DTC-GPC kernels (k_dtc_filter + k_dtc): ise (n x ny), status, y, u."""
+    from mpcgpu.dtcgpc import DtcProblemStruct
+    ny, nu = prob.pnz.a.shape
+    nq = prob.pq.a.shape[1]
+    nit = int(prob.nit)
+    f64 = lambda x: np.ascontiguousarray(np.asarray(x, dtype=np.float64))
+    i32 = lambda x: np.ascontiguousarray(np.asarray(x, dtype=np.int32))
+    keep = dict(ma=f64(prob.pnz.a), mb0=f64(prob.pnz.b0), mb1=f64(prob.pnz.b1), md=i32(prob.pnz.d),
+                pa=f64(prob.preal.a), pb0=f64(prob.preal.b0), pb1=f64(prob.preal.b1), pd=i32(prob.preal.d),
+                qa=f64(prob.pq.a), qb0=f64(prob.pq.b0), qb1=f64(prob.pq.b1), qd=i32(prob.pq.d),
+                L=f64(prob.L), R=f64(prob.R), r=f64(prob.r).reshape(ny, nit), q=f64(prob.q).reshape(nq, nit))
+    ps = DtcProblemStruct(ny, nu, nq, nit, int(prob.pmax), int(prob.mmax), int(prob.k_start), 0)
+    for k, arr in keep.items():
+        setattr(ps, k, arr.ctypes.data if arr.size else None)
+    p = i32(np.atleast_2d(p)); n = p.shape[0]
+    m = i32(np.atleast_2d(m)); dl = f64(delta).reshape(n, ny); lm = f64(lam).reshape(n, nu)
+    al = f64(np.broadcast_to(alfa, (n,))); ra = f64(np.broadcast_to(raio, (n,)))
+    ise = np.zeros((n, ny)); status = np.full(n, -1, dtype=np.int32)
+    y = np.zeros((n, ny, nit)) if traj else None
+    u = np.zeros((n, nu, nit)) if traj else None
+    P = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None else None
+    err = C.create_string_buffer(256)
+    rc = lib().emu_dtc_eval(C.byref(ps), n, P(p), P(m), P(dl), P(lm), P(al), P(ra), P(ise), P(y), P(u), P(status), err, 256)
+    if rc:
+        raise RuntimeError(err.value.decode())
+    return ise, status, y, u

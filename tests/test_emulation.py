@@ -173,3 +173,27 @@ def test_nmpc_groups_of_a_warp_may_diverge(G):
     assert np.array_equal(c, c1)                                            # the group width does not change the arithmetic
     assert (np.abs(c - c0) / np.abs(c0)).max() < 1e-6
     assert (np.abs(c - gold["gam"][:4]) / np.abs(gold["gam"][:4])).max() < 1e-5
+
+
+@pytest.mark.parametrize("deltak,deltaL", [(0.0, 0.0), (0.1, 1.0)])
+def test_dtc_kernels_on_the_host(deltak, deltaL):
+    """csrc/mpc_dtc_kernel.cuh (k_dtc_filter: robustness filter per candidate; k_dtc: gain, predictor and loop, one warp per
+    candidate, four candidates per CTA) executed by host threads against oracle/dtc_gpc_oracle.py, the line-by-line numpy
+    restatement of DTC_GPC_WW.m -- nominal plant and the reference's mismatch knobs (unstable tunings of the sweep are
+    compared relative to the size of their response)."""
+    from mpcgpu.dtcgpc import woodberry_dtc, synthetic_dtc_population
+    from oracle import dtc_gpc_oracle as dorc
+    prob = woodberry_dtc(deltak=deltak, deltaL=deltaL)
+    p, m, dl, lm, alfa, raio = synthetic_dtc_population(prob, 9, seed=3)      # 9: a partly filled CTA too
+    raio[0] = 0.999      # no slow pole: Fr = 1
+    raio[1] = 0.5        # every pole counts as slow
+    p[2] = (3, 3); m[2] = (3, 3); dl[2] = 1.0; lm[2] = 1.0; alfa[2] = 0.7; raio[2] = 0.8     # the script's own tuning (DTC_GPC_WW.m:56-76)
+    ise, st, y, u = emu.dtc_eval(prob, p, m, dl, lm, alfa, raio)
+    assert (st == 0).all(), st
+    for c in range(len(p)):
+        fr = dorc.mimofilter_Fr(prob.pnz, alfa[c], raio[c])
+        y0, u0 = dorc.dtc_gpc_closed_loop(prob, p[c], m[c], dl[c], lm[c], fr)
+        sc = max(1.0, np.abs(y0).max(), np.abs(u0).max())
+        assert np.abs(y[c] - y0).max() < 1e-8 * sc and np.abs(u[c] - u0).max() < 1e-8 * sc, (c, np.abs(y[c] - y0).max(), sc)
+        if sc < 1e3:
+            np.testing.assert_allclose(ise[c], ((y0 - prob.r) ** 2).sum(axis=1), rtol=1e-8)
