@@ -360,6 +360,7 @@ template <int G>
 __device__ __noinline__ int nmg_nlmpcmove(const NmpcDev &D, const double *x0, const double *uprev, const double *r, int p, int m, const double *wy2,
                              const double *wu2, const NmgSm &sm, const NmGroup<G> &gp, unsigned *n_sqp) {
     const int nz = NU * m, gl = gp.gl;
+    gp.sync();   // every lane has read what it wanted from the previous plan (the caller takes u(k) = v[0..1] from it)
     for (int a = gl; a < nz; a += G) { sm.v[a] = nmg_clamp(sm.v[a], D.umin[a & 1], D.umax[a & 1]); sm.d[a] = 0.0; }
     gp.sync();
     double Jcur = nmg_model<G>(D, x0, uprev, r, p, m, wy2, wu2, sm, gp, 0.0);
