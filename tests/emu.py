@@ -115,3 +115,21 @@ def dtc_eval(prob, p, m, delta, lam, alfa, raio, traj=True):
     if rc:
         raise RuntimeError(err.value.decode())
     return ise, status, y, u
+
+
+def build_matrices(prob, p, m, P, delta, lam, threads=0):
+    """The builder's output (M: nst x R as [col][row], W: 2R x R) for one candidate: threads=0 the serial host build of
+    mpc_core.cuh, threads=128 the same source executed by that many host threads with real block barriers."""
+    ps, keep = make_problem_struct(prob)
+    R = prob.nu * P
+    dl = np.ascontiguousarray(delta, dtype=np.float64); lm = np.ascontiguousarray(lam, dtype=np.float64)
+    Mg = np.zeros(256 * R); Wg = np.zeros(2 * R * R)
+    err = C.create_string_buffer(256)
+    Pp = lambda a: a.ctypes.data_as(C.c_void_p)
+    if threads:
+        rc = lib().emu_build_threads(C.byref(ps), int(p), int(m), int(P), Pp(dl), Pp(lm), Pp(Mg), Pp(Wg), int(threads), err, 256)
+    else:
+        rc = lib().emu_build_serial(C.byref(ps), int(p), int(m), int(P), Pp(dl), Pp(lm), Pp(Mg), Pp(Wg), err, 256)
+    if rc < 0:
+        raise RuntimeError(err.value.decode())
+    return Mg, Wg, rc

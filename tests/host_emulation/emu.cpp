@@ -195,6 +195,20 @@ extern "C" int emu_eval_est(const mpcgpu_problem *pb, const double *pa, const do
     return run_block(nu, P, L, T, N, Nu, Mg.data(), Wg.data(), 1, -2, out, &E, delta);
 }
 
+// the builder's output for one candidate from the SERIAL host build of mpc_core.cuh (emu_build.cpp runs the same source with threads)
+extern "C" int emu_build_serial(const mpcgpu_problem *pb, int p, int m, int P, const double *delta, const double *lambda, double *Mg,
+                                double *Wg, char *err, int errlen) {
+    MpcHostTables ht;
+    std::string e = mpc_build_tables(*pb, ht);
+    if (!e.empty()) { std::strncpy(err, e.c_str(), errlen - 1); return -1; }
+    const MpcLayout &L = ht.L;
+    MpcTables T{ht.TG.data(), ht.TK.data(), ht.S1.data(), ht.r.data(), ht.v.data(), ht.yref.data(),
+                ht.step.data(), ht.pa.data(), L.pmax + L.mmax + 2, ht.sig.data()};
+    std::vector<double> bsm(mpc_builder_smem_doubles(L.nu * m, L.nst));
+    int flag = 0;
+    return mpc_build_candidate(L, T, p, m, P, delta, lambda, bsm.data(), Mg, Wg, &flag);
+}
+
 // shared-memory footprint of one closed-loop run (bytes) for padded control horizon P: occupancy bookkeeping
 extern "C" long long emu_sim_smem_bytes(const mpcgpu_problem *pb, int P) {
     MpcHostTables ht;

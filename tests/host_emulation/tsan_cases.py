@@ -53,3 +53,8 @@ elif which == "nmpc_vns":
     from mpcgpu.nmpc import vandevusse
     p = vandevusse()
     print("ok", emu.nmpc_eval(p, 6, 2, [1.0, 1.0], [0.1, 0.1], mode="vns")[0])
+elif which == "build":
+    import mpcgpu
+    p = mpcgpu.shell3x3(2)
+    M, W, rc = emu.build_matrices(p, 60, 9, 16, np.array([0.4, 1.0, 0.2]), np.array([0.1, 0.3, 0.05]), threads=128)
+    print("ok", rc, float(np.abs(W).max()))

@@ -197,3 +197,19 @@ def test_dtc_kernels_on_the_host(deltak, deltaL):
         assert np.abs(y[c] - y0).max() < 1e-8 * sc and np.abs(u[c] - u0).max() < 1e-8 * sc, (c, np.abs(y[c] - y0).max(), sc)
         if sc < 1e3:
             np.testing.assert_allclose(ise[c], ((y0 - prob.r) ** 2).sum(axis=1), rtol=1e-8)
+
+
+@pytest.mark.parametrize("case", ["shell3x3", "shell7x5"])
+def test_builder_with_real_threads(case):
+    """csrc/mpc_core.cuh (k_build's body: Hessian from the prefix-Gram tables, Cholesky, [M | W] = H^-1 [-K | I]) executed by 128
+    host threads with real block barriers gives, bit for bit, what the serial host build of the same source gives."""
+    import mpcgpu
+    p = {"shell3x3": lambda: shell3x3(2), "shell7x5": mpcgpu.shell7x5}[case]()
+    for N, Nu in ((40, 6), (127, 15), (9, 2)):
+        dl = np.zeros(p.ny) if case == "shell7x5" else np.linspace(0.2, 1.5, p.ny)
+        lm = np.linspace(0.05, 0.7, p.nu)
+        M0, W0, rc0 = emu.build_matrices(p, N, Nu, 16, dl, lm, threads=0)
+        M1, W1, rc1 = emu.build_matrices(p, N, Nu, 16, dl, lm, threads=128)
+        assert rc0 == 0 and rc1 == 0
+        assert np.array_equal(M0, M1) and np.array_equal(W0, W1)
+        assert np.abs(W0).max() > 0 and (case == "shell7x5" or np.abs(M0).max() > 0)
