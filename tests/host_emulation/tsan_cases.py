@@ -58,3 +58,8 @@ elif which == "build":
     p = mpcgpu.shell3x3(2)
     M, W, rc = emu.build_matrices(p, 60, 9, 16, np.array([0.4, 1.0, 0.2]), np.array([0.1, 0.3, 0.05]), threads=128)
     print("ok", rc, float(np.abs(W).max()))
+elif which == "soft_idx":
+    import mpcgpu, copy
+    p = copy.copy(mpcgpu.shell7x5()); p.nit = 40; p.r = p.r[:40].copy(); p.v = p.v[:40].copy(); p.yref = p.yref[:, :40].copy()
+    N, Nu, dl, lm = mpcgpu.synthetic_population(p, 1, seed=5, wlo=1e-2); N[0] = 9; Nu[0] = 7      # p < 1.5 m: horizon-order pivoting
+    print("ok", emu.eval_batch(p, N, Nu, dl, lm, "gam")[0])
