@@ -193,6 +193,22 @@ def cpu_reference_rate(prob, N, Nu, delta, lam, mode, budget_s=12.0, nthreads=0)
     return n / dt, cores, n
 
 
+def linear_config(args, world, n, nit):
+    """`config` of the bench line: ONE function for both arms, so that the driver's same-config check compares equal dicts.  The L2
+    and multi-GPU entries describe how the GPU arm is measured; the reference arm (host CPU) carries them unchanged."""
+    return {"workload": workload_string(args.mode, args.pop, args.config),
+            "population_per_gpu": int(n), "nit": int(nit), "cost_mode": args.mode,
+            "l2": "GPU arm: flushed between timed steps (256 MiB write, untimed); reference arm: host CPU, not applicable",
+            "multi_gpu": ("population dealt over the ranks by estimated work (sorted round-robin, mpcgpu.distributed), "
+                          "one NCCL all-gather of fitness per step") if world > 1 else "single GPU"}
+
+
+def other_config(args, n):
+    return {"workload": other_workload(args), "population_per_gpu": int(n),
+            "value_is": "GPU arm: device time of the kernel (CUDA events inside the C ABI call, inputs resident); reference arm: wall clock",
+            "l2": "GPU arm: flushed between timed steps (256 MiB write, untimed); reference arm: host CPU, not applicable"}
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU implementation of the path.  MATLAB + the closed-source MPC
     Toolbox cannot run here, so this is the oracle port on all host threads."""
@@ -225,7 +241,8 @@ def run_reference(args):
     line = {"impl": "reference", "metric": metric_name(args), "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_string(args.mode, args.pop, args.config), "impl": "CPU oracle port (the reference's MATLAB + MPC Toolbox cannot run here)", "sample": sample},
+            "config": linear_config(args, world, len(N), prob.nit),
+            "reference_note": "CPU oracle port (the reference's MATLAB + MPC Toolbox cannot run here); " + sample,
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "qp_solves_per_s": val * (500 if args.mode == "gam" else 3 * 501)}
@@ -308,7 +325,7 @@ def run_other(args):
         print(json.dumps({"impl": "reference", "metric": metric_name(args), "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
                           "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
                           "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                          "config": {"workload": other_workload(args), "impl": kind_note, "sample": sample},
+                          "config": other_config(args, args.pop), "reference_note": kind_note + "; " + sample,
                           "cpu_baseline": {"value": val, "unit": UNIT, "cores": c_, "kind": "port", "sample": sample},
                           "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
         return
@@ -362,9 +379,7 @@ def run_other(args):
         line = {"metric": metric_name(args), "value": n * world * args.steps / (kern_ms * 1e-3), "unit": UNIT, "n_gpus": world,
                 "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": kern_ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": other_workload(args), "population_per_gpu": n,
-                           "value_is": "device time of the kernel (CUDA events inside the C ABI call, inputs resident)",
-                           "l2": "flushed between timed steps (256 MiB write, untimed)"},
+                "config": other_config(args, n),
                 "e2e": {"value": n * world * args.steps / (wall_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                         "d2h_bytes_per_step": int(n * width * 8 + n * 4), "timing": "wall clock around the synchronous C-ABI call"},
                 "gpu_launches": int(c1["kernel_launches"] - c0["kernel_launches"]),
@@ -570,11 +585,7 @@ def main():
             "metric": metric_name(args), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_string(args.mode, args.pop, args.config),
-                       "population_per_gpu": n, "nit": nit, "cost_mode": args.mode,
-                       "l2": "flushed between timed steps (256 MiB write, untimed)",
-                       "multi_gpu": ("population dealt over the ranks by estimated work (sorted round-robin, mpcgpu.distributed), "
-                                     "one NCCL all-gather of fitness per step") if world > 1 else "single GPU"},
+            "config": linear_config(args, world, n, nit),
             "qp_solves_per_s": value * runs * (nit + (1 if args.mode == "vns" else 0)),
             "per_rank_ms": {"kernel_ms": [round(per_rank[2 * r_], 4) for r_ in range(world)],
                             "allgather_ms_incl_wait_for_slowest_rank": [round(per_rank[2 * r_ + 1], 4) for r_ in range(world)]},
