@@ -172,6 +172,16 @@ def other_configs():
         en.close()
     except Exception as exc:   # context only: never fail the headline line
         out["error"] = repr(exc)
+    try:   # single-shooting NMPC sweep (`Explicit NMPC/`): k_ssnmpc, one thread per closed loop of 150 samples
+        ps = mpcgpu.explicit_nmpc(); es = mpcgpu.SsnmpcEvaluator(ps, device=0)
+        Ps = mpcgpu.synthetic_ssnmpc_population(ps, 4096, seed=0)
+        es.eval_batch(*[a[:64] for a in Ps])
+        t0 = time.perf_counter(); os_ = es.eval_batch(*Ps); dt = time.perf_counter() - t0
+        out["explicit_nmpc_single_shooting"] = {"candidates": 4096, "candidates_per_s": 4096 / dt, "failed": int((os_["status"] != 0).sum()),
+                                                "controller_calls": es.counters()["qp_solves"]}
+        es.close()
+    except Exception as exc:
+        out["explicit_nmpc_error"] = repr(exc)
     return out
 
 

@@ -271,6 +271,41 @@ int mpcgpu_nmpc_eval_batch(mpcgpu_nmpc_handle *h, int n, const int32_t *N, const
 int mpcgpu_nmpc_get_counters(mpcgpu_nmpc_handle *h, mpcgpu_counters *out); /* qp_solves = controller calls, as_iterations = SQP iterations */
 const char *mpcgpu_nmpc_last_error(mpcgpu_nmpc_handle *h);
 
+/* ------------------------------------------------------------------------------------------------
+ * Single-shooting NMPC: batched
+ *   [y, u] = ClosedLoopNMPC(x0_model, x_control, u0, r, N, Nu, Q, W, nit, ub1, lb1, inK, Ts)
+ *        /root/reference/Explicit NMPC/ClosedLoopNMPC.m:1
+ * whose controller call is  duOt = NMPC_Controller(Par)  (/root/reference/Explicit NMPC/NMPC_Controller.m:1): per input a
+ * block of Nu_j offsets from u_j(k-1), cost sum_j Q_j sum_i (r_j(k) - (y_j(k+i) + n_j))^2 + sum_j W_j sum_c X_jc^2 (weights
+ * not squared, :128-138), n_j the model-deviation term of :106-123, bounds lb - u(k-1) <= X <= ub - u(k-1), start X = 0.
+ * Plant and model: plant_model.m:1-56 (= the Van de Vusse right-hand side above), RK4 with `nsub` sub-steps where the
+ * reference calls ode23t / ode45; minimiser by Gauss-Newton with an exact box-QP step where the reference calls fmincon-SQP
+ * (csrc/mpc_ssnmpc_core.h: S1-S5).  The reference's loop adds 0.01*randn to the plant state every sample
+ * (ClosedLoopNMPC.m:88-90): here the draws are an argument (`noise`), NULL = none.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t nit, pmax;           /* samples; largest prediction horizon a candidate may ask for               */
+    int32_t inK;                 /* 1-based first simulated sample (main.m:52: 4)                             */
+    int32_t nsub, max_sqp;       /* RK4 sub-steps per sample; Gauss-Newton iteration cap per controller call  */
+    int32_t model;               /* MPCGPU_MODEL_VANDEVUSSE                                                   */
+    int32_t x_control[2];        /* 0-based indices of the controlled states (main.m:75: [2 3] -> {1, 2})     */
+    double Ts;
+    const double *x0, *u0;       /* x0_model (3), u0 (2)                                                      */
+    const double *lb, *ub;       /* lb1, ub1 (2)                                                              */
+    const double *r;             /* 2 x nit set-point, signals x time                                         */
+} mpcgpu_ssnmpc_problem;
+typedef struct mpcgpu_ssnmpc_handle mpcgpu_ssnmpc_handle;
+int mpcgpu_ssnmpc_create(const mpcgpu_ssnmpc_problem *problem, int device, mpcgpu_ssnmpc_handle **out);
+void mpcgpu_ssnmpc_destroy(mpcgpu_ssnmpc_handle *h);
+/* N: n (1 <= N <= pmax); Nu: n x 2 row-major, per-input control horizons (1 <= Nu_j <= N, sum <= 30); Q, W: n x 2;
+ * r_override: NULL or 2 x nit; noise: NULL or 3 x nit (added to the plant state after the step of sample k);
+ * cost: NULL or n x 2 = sum over k = inK..nit of (y_j(k) - r_j(k))^2 (NaN when status != 0); y, u: NULL or n x 2 x nit;
+ * status: NULL or n (MPCGPU_CAND_*: 0 ok, 2 / 3 box-QP failure, 4 invalid horizons). */
+int mpcgpu_ssnmpc_eval_batch(mpcgpu_ssnmpc_handle *h, int n, const int32_t *N, const int32_t *Nu, const double *Q, const double *W,
+                             const double *r_override, const double *noise, double *cost, double *y, double *u, int32_t *status);
+int mpcgpu_ssnmpc_get_counters(mpcgpu_ssnmpc_handle *h, mpcgpu_counters *out); /* qp_solves = controller calls, as_iterations = Gauss-Newton iterations */
+const char *mpcgpu_ssnmpc_last_error(mpcgpu_ssnmpc_handle *h);
+
 #ifdef __cplusplus
 }
 #endif

@@ -31,6 +31,12 @@
  *     [cost, status] = mpcgpu_mex('nmpc_eval', hn, N, Nu, delta, lambda, mode)
  *     [y,u,yopt,uopt] = mpcgpu_mex('nmpc_closedloop', hn, r, N, Nu, delta, lambda, nit)   r: 2 x nit (either orientation)
  *     mpcgpu_mex('nmpc_destroy', hn)
+ *   single-shooting NMPC (Explicit NMPC/ClosedLoopNMPC.m:1, NMPC_Controller.m:1)
+ *     hs = mpcgpu_mex('ssnmpc_create', Ps)              Ps: struct with the fields of mpcgpu_ssnmpc_problem (x_control 1-based)
+ *     [cost, status] = mpcgpu_mex('ssnmpc_eval', hs, N, Nu, Q, W)                 N n x 1, Nu / Q / W n x 2: a sweep
+ *     [y, u] = mpcgpu_mex('ssnmpc_closedloop', hs, r, N, Nu, Q, W [, noise])      one run; r 2 x nit, noise 3 x nit (the randn
+ *                      draws of ClosedLoopNMPC.m:89, already scaled), either orientation
+ *     mpcgpu_mex('ssnmpc_destroy', hs)
  *   DTC-GPC sweep (DTC-GPC/DTC_GPC_WW.m:56-164)
  *     hd = mpcgpu_mex('dtc_create', Pd)                 Pd: struct with the fields of mpcgpu_dtc_problem
  *     [ise, status, y, u] = mpcgpu_mex('dtc_eval', hd, p, m, delta, lambda, fr_num, fr_den, fr_len)
@@ -145,6 +151,7 @@ static void remember(void *h, double Ts, int ny, int nu, int nd) {
 }
 static int lookup(void *h) { for (int i = 0; i < MAX_HANDLES; ++i) if (g_lin[i].h == h) return i; return -1; }
 static void forget(void *h) { const int i = lookup(h); if (i >= 0) g_lin[i].h = NULL; }
+static int nit_of(void *h) { const int i = lookup(h); return i >= 0 ? g_lin[i].nd : 0; }   /* handles whose nd slot keeps nit */
 
 static void fill_problem(const mxArray *P, mpcgpu_problem *pb, int32_t **d, int32_t **dmin) {
     memset(pb, 0, sizeof(*pb));
@@ -314,6 +321,74 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
         mxFree(rt); mxFree(r);
     } else if (!strcmp(cmd, "nmpc_destroy")) {
         void *h = handle_of(prhs[1]); forget(h); mpcgpu_nmpc_destroy((mpcgpu_nmpc_handle *)h);
+    /* ------------------------------------------------ single-shooting NMPC ------------------------------------------------ */
+    } else if (!strcmp(cmd, "ssnmpc_create")) {
+        ARG(nrhs >= 2 && mxIsStruct(prhs[1]), "ssnmpc_create: problem struct expected");
+        const mxArray *P = prhs[1];
+        mpcgpu_ssnmpc_problem pb;
+        memset(&pb, 0, sizeof(pb));
+        pb.nit = scalar_i(P, "nit"); pb.pmax = field(P, "pmax", 0) ? scalar_i(P, "pmax") : 31; pb.inK = scalar_i(P, "inK");
+        pb.nsub = field(P, "nsub", 0) ? scalar_i(P, "nsub") : 4; pb.max_sqp = field(P, "max_sqp", 0) ? scalar_i(P, "max_sqp") : 400;
+        pb.model = MPCGPU_MODEL_VANDEVUSSE; pb.Ts = mxGetScalar(field(P, "Ts", 1));
+        {
+            mwSize nxc; int32_t *xc = as_i32(field(P, "x_control", 1), &nxc);
+            ARG(nxc == 2, "x_control must have 2 entries");
+            pb.x_control[0] = xc[0] - 1; pb.x_control[1] = xc[1] - 1;      /* MATLAB indices */
+            mxFree(xc);
+        }
+        pb.x0 = f64(P, "x0", 1); pb.u0 = f64(P, "u0", 1); pb.lb = f64(P, "lb", 1); pb.ub = f64(P, "ub", 1);
+        pb.r = f64(P, "r", 1);                                             /* 2 x nit, row-major (signals x time) */
+        mpcgpu_ssnmpc_handle *h = NULL;
+        if (mpcgpu_ssnmpc_create(&pb, nrhs > 2 ? (int)mxGetScalar(prhs[2]) : -1, &h) != MPCGPU_OK)
+            mexErrMsgIdAndTxt("mpcgpu:create", "%s", mpcgpu_ssnmpc_last_error(NULL));
+        remember(h, pb.Ts, 2, 2, pb.nit);
+        plhs[0] = handle_out(h);
+    } else if (!strcmp(cmd, "ssnmpc_eval")) {
+        ARG(nrhs == 6, "ssnmpc_eval: (h, N, Nu, Q, W)");
+        mpcgpu_ssnmpc_handle *h = (mpcgpu_ssnmpc_handle *)handle_of(prhs[1]);
+        mwSize n, n2;
+        int32_t *N = as_i32(prhs[2], &n), *NuC = as_i32(prhs[3], &n2);
+        ARG(n2 == 2 * n, "Nu must be n x 2");
+        int32_t *Nu = (int32_t *)mxMalloc(sizeof(int32_t) * (n2 ? n2 : 1));
+        for (mwSize c = 0; c < n; ++c) { Nu[2 * c] = NuC[c]; Nu[2 * c + 1] = NuC[n + c]; }   /* column-major -> candidate rows */
+        double *Q = rows_of(prhs[4], n, 2), *W = rows_of(prhs[5], n, 2);
+        double *cost = (double *)mxMalloc(sizeof(double) * ((n * 2) > 0 ? n * 2 : 1));
+        int32_t *st = (int32_t *)mxMalloc(sizeof(int32_t) * (n ? n : 1));
+        if (mpcgpu_ssnmpc_eval_batch(h, (int)n, N, Nu, Q, W, NULL, NULL, cost, NULL, NULL, st) != MPCGPU_OK)
+            mexErrMsgIdAndTxt("mpcgpu:eval", "%s", mpcgpu_ssnmpc_last_error(h));
+        cost_out(nlhs, plhs, cost, st, n, 2);
+        mxFree(N); mxFree(NuC); mxFree(Nu); mxFree(Q); mxFree(W); mxFree(cost); mxFree(st);
+    } else if (!strcmp(cmd, "ssnmpc_closedloop")) {
+        /* [y, u] = ssnmpc_closedloop(h, r, N, Nu, Q, W [, noise]) -- ClosedLoopNMPC.m:1 */
+        ARG(nrhs == 7 || nrhs == 8, "ssnmpc_closedloop: (h, r, N, Nu, Q, W [, noise])");
+        mpcgpu_ssnmpc_handle *h = (mpcgpu_ssnmpc_handle *)handle_of(prhs[1]);
+        const int nit = nit_of(h);
+        ARG(nit > 0, "unknown handle");
+        double *rt = time_major(prhs[2], nit, 2);                          /* nit x 2 */
+        double *r = (double *)mxMalloc(sizeof(double) * 2 * nit);          /* ABI: 2 x nit */
+        for (int k = 0; k < nit; ++k) { r[k] = rt[2 * k]; r[nit + k] = rt[2 * k + 1]; }
+        double *nz = NULL;
+        if (nrhs == 8 && mxGetNumberOfElements(prhs[7])) {
+            double *nt = time_major(prhs[7], nit, 3);
+            nz = (double *)mxMalloc(sizeof(double) * 3 * nit);
+            for (int k = 0; k < nit; ++k) for (int i = 0; i < 3; ++i) nz[i * nit + k] = nt[3 * k + i];
+            mxFree(nt);
+        }
+        mwSize nn; int32_t *Nv = as_i32(prhs[3], &nn);
+        ARG(nn >= 1, "N missing");
+        const int32_t N = Nv[0];                                           /* Q(i)*eye(N(1)), ClosedLoopNMPC.m:37 */
+        mwSize nnu; int32_t *Nu = as_i32(prhs[4], &nnu);
+        ARG(nnu == 2 && mxGetNumberOfElements(prhs[5]) == 2 && mxGetNumberOfElements(prhs[6]) == 2, "Nu, Q and W must have 2 entries");
+        int32_t st = 0;
+        double *y = (double *)mxMalloc(sizeof(double) * 2 * nit), *u = (double *)mxMalloc(sizeof(double) * 2 * nit);
+        if (mpcgpu_ssnmpc_eval_batch(h, 1, &N, Nu, mxGetPr(prhs[5]), mxGetPr(prhs[6]), r, nz, NULL, y, u, &st) != MPCGPU_OK)
+            mexErrMsgIdAndTxt("mpcgpu:eval", "%s", mpcgpu_ssnmpc_last_error(h));
+        if (st) mexErrMsgIdAndTxt("mpcgpu:candidate", "Error in closed-loop simulation (status %d)", (int)st);
+        plhs[0] = sig_out(y, 2, nit);
+        if (nlhs > 1) plhs[1] = sig_out(u, 2, nit);
+        mxFree(rt); mxFree(r); if (nz) mxFree(nz); mxFree(Nv); mxFree(Nu); mxFree(y); mxFree(u);
+    } else if (!strcmp(cmd, "ssnmpc_destroy")) {
+        void *h = handle_of(prhs[1]); forget(h); mpcgpu_ssnmpc_destroy((mpcgpu_ssnmpc_handle *)h);
     /* ------------------------------------------------ DTC-GPC sweep ------------------------------------------------ */
     } else if (!strcmp(cmd, "dtc_create")) {
         ARG(nrhs >= 2 && mxIsStruct(prhs[1]), "dtc_create: problem struct expected");

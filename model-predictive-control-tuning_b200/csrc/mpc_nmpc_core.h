@@ -5,10 +5,12 @@
 // candidates).  The scipy-based checker of the tests stays the independent reference for parity.
 #pragma once
 #include <math.h>
+#ifndef NM_FN   /* a second translation unit of the library defines it `static __device__` (mpc_ssnmpc.cu) */
 #ifdef __CUDACC__
 #define NM_FN __device__
 #else
 #define NM_FN static inline
+#endif
 #endif
 
 #define NX 3

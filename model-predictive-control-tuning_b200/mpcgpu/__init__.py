@@ -5,3 +5,4 @@ from .api import Evaluator, MultiEvaluator, MpcGpuError, closedloop_toolbox, gam
 from .dtcgpc import DtcProblem, DtcEvaluator, woodberry_dtc, synthetic_dtc_population, robustness_filter, mimo_filter, dtc_gpc_ww  # noqa: F401
 from .nmpc import NmpcProblem, NmpcEvaluator, vandevusse, synthetic_nmpc_population, closedloop_toolbox_nmpc  # noqa: F401
 from . import tuner  # noqa: F401
+from .ssnmpc import SsnmpcProblem, SsnmpcEvaluator, explicit_nmpc, synthetic_ssnmpc_population, ClosedLoopNMPC  # noqa: F401

@@ -116,6 +116,13 @@ def load_library():
     lib.mpcgpu_nmpc_destroy.restype = None
     lib.mpcgpu_nmpc_eval_batch.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 7
     lib.mpcgpu_nmpc_get_counters.argtypes = [C.c_void_p, C.POINTER(Counters)]
+    lib.mpcgpu_ssnmpc_last_error.restype = C.c_char_p
+    lib.mpcgpu_ssnmpc_last_error.argtypes = [C.c_void_p]
+    lib.mpcgpu_ssnmpc_create.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
+    lib.mpcgpu_ssnmpc_destroy.argtypes = [C.c_void_p]
+    lib.mpcgpu_ssnmpc_destroy.restype = None
+    lib.mpcgpu_ssnmpc_eval_batch.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 10
+    lib.mpcgpu_ssnmpc_get_counters.argtypes = [C.c_void_p, C.POINTER(Counters)]
     _lib = lib
     return lib
 
@@ -130,4 +137,5 @@ EXPORTED_SYMBOLS = [
     "mpcgpu_dtc_create", "mpcgpu_dtc_destroy", "mpcgpu_dtc_eval_batch", "mpcgpu_dtc_eval_batch_design", "mpcgpu_dtc_last_error",
     "mpcgpu_dtc_host_tables", "mpcgpu_dtc_get_counters",
     "mpcgpu_nmpc_create", "mpcgpu_nmpc_destroy", "mpcgpu_nmpc_eval_batch", "mpcgpu_nmpc_get_counters", "mpcgpu_nmpc_last_error",
+    "mpcgpu_ssnmpc_create", "mpcgpu_ssnmpc_destroy", "mpcgpu_ssnmpc_eval_batch", "mpcgpu_ssnmpc_get_counters", "mpcgpu_ssnmpc_last_error",
 ]

@@ -12,6 +12,7 @@
 #include <omp.h>
 #endif
 #include "../model-predictive-control-tuning_b200/csrc/mpc_nmpc_core.h"
+#include "../model-predictive-control-tuning_b200/csrc/mpc_ssnmpc_core.h"
 
 extern "C" int nmpc_port_eval_batch(int nit, int pmax, int mmax, int inK, int nsub, int max_sqp, double Ts, const double *x0,
                                     const double *u0, const double *umin, const double *umax, const double *xmin,
@@ -55,4 +56,62 @@ extern "C" int nmpc_port_eval_batch(int nit, int pmax, int mmax, int inK, int ns
         }
     }
     return 0;
+}
+
+// Single-shooting formulation (`Explicit NMPC/`, csrc/mpc_ssnmpc_core.h) compiled for the host: the code of k_ssnmpc run per
+// candidate with OpenMP.  Nu: n x 2 (per-input control horizons), Q, W: n x 2; noise: nx x nit or NULL; cost: n x 2 or NULL;
+// y, u: n x 2 x nit or NULL.
+extern "C" int ssnmpc_port_eval_batch(int nit, int pmax, int inK, int nsub, int max_sqp, double Ts, const double *x0, const double *u0,
+                                      const double *lb, const double *ub, const int *xc, const double *r, const double *noise, int n,
+                                      const int *N, const int *Nu, const double *Q, const double *W, double *cost, double *y, double *u,
+                                      int *status, int nthreads) {
+    SsnmpcDev S;
+    NmpcDev &D = S.D;
+    D.nit = nit; D.pmax = pmax; D.mmax = NM_MAXM; D.inK = inK; D.nsub = nsub; D.max_sqp = max_sqp; D.Ts = Ts;
+    for (int i = 0; i < NX; ++i) { D.x0[i] = x0[i]; D.xmin[i] = -INFINITY; D.xmax[i] = INFINITY; }
+    for (int j = 0; j < NU; ++j) { D.u0[j] = u0[j]; D.umin[j] = lb[j]; D.umax[j] = ub[j]; D.su[j] = ub[j] - lb[j]; }
+    for (int j = 0; j < NY; ++j) { D.sy[j] = 1.0; S.xc[j] = xc[j]; }
+    S.pmax = pmax;
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+#pragma omp parallel
+    {
+        std::vector<double> H(NM_LD * NM_LD), Lc(NM_LD * NM_LD);
+#pragma omp for schedule(dynamic, 1)
+        for (int c = 0; c < n; ++c) {
+            const int p = N[c], *nuj = Nu + (size_t)c * NU;
+            bool ok = p >= 1 && p <= pmax;
+            int nz = 0;
+            for (int j = 0; j < NU; ++j) { ok = ok && nuj[j] >= 1 && nuj[j] <= p; nz += nuj[j]; }
+            if (!ok || nz > NM_MAXZ) {
+                status[c] = 4;
+                if (cost) for (int j = 0; j < NY; ++j) cost[(size_t)c * NY + j] = NAN;
+                continue;
+            }
+            unsigned nc = 0, ns = 0;
+            status[c] = ssnmpc_run(S, p, nuj, Q + (size_t)c * NY, W + (size_t)c * NU, r, noise, y ? y + (size_t)c * NY * nit : nullptr,
+                                   u ? u + (size_t)c * NU * nit : nullptr, cost ? cost + (size_t)c * NY : nullptr, H.data(), Lc.data(),
+                                   &nc, &ns);
+        }
+    }
+    return 0;
+}
+
+// one NMPC_Controller call of the host build (tests compare it with the scipy minimiser on the same objective); X: sum(Nu)
+extern "C" int ssnmpc_port_controller(int nsub, int max_sqp, double Ts, const double *lb, const double *ub, const int *xc,
+                                      const double *x, const double *uprev, const double *r, int N, const int *Nu, const double *Q,
+                                      const double *W, double *X, int *n_sqp) {
+    SsnmpcDev S;
+    NmpcDev &D = S.D;
+    D.nit = 0; D.pmax = N; D.mmax = NM_MAXM; D.inK = 1; D.nsub = nsub; D.max_sqp = max_sqp; D.Ts = Ts;
+    for (int i = 0; i < NX; ++i) { D.x0[i] = x[i]; D.xmin[i] = -INFINITY; D.xmax[i] = INFINITY; }
+    for (int j = 0; j < NU; ++j) { D.u0[j] = uprev[j]; D.umin[j] = lb[j]; D.umax[j] = ub[j]; D.su[j] = ub[j] - lb[j]; }
+    for (int j = 0; j < NY; ++j) { D.sy[j] = 1.0; S.xc[j] = xc[j]; }
+    S.pmax = N;
+    std::vector<double> H(NM_LD * NM_LD), Lc(NM_LD * NM_LD);
+    unsigned ns = 0;
+    const int rc = ss_controller(S, x, uprev, r, N, Nu, Q, W, X, H.data(), Lc.data(), &ns);
+    *n_sqp = (int)ns;
+    return rc;
 }

@@ -33,3 +33,37 @@ def eval_batch(prob, N, Nu, delta, lam, mode="gam", nthreads=0):
                                *[P(b) for b in bufs], C.c_int(n), P(N), P(Nu), P(dl), P(lm), C.c_int(m), P(cost), P(status),
                                C.c_int(int(nthreads)))
     return cost, status
+
+
+def ssnmpc_eval_batch(prob, N, Nu, Q, W, noise=None, traj=False, nthreads=0):
+    """Host build of csrc/mpc_ssnmpc_core.h (the single-shooting formulation).  prob: an SsnmpcProblem-shaped object.
+    Returns (cost n x 2, status[, y, u])."""
+    f64 = lambda x: np.ascontiguousarray(np.asarray(x, dtype=np.float64))
+    N = np.ascontiguousarray(np.atleast_1d(N), dtype=np.int32); n = len(N)
+    Nu = np.ascontiguousarray(Nu, dtype=np.int32).reshape(n, 2)
+    Qa = f64(Q).reshape(n, 2); Wa = f64(W).reshape(n, 2)
+    x0, u0, lb, ub, r = f64(prob.x0), f64(prob.u0), f64(prob.lb), f64(prob.ub), f64(prob.r)
+    xc = np.ascontiguousarray(prob.x_control, dtype=np.int32)
+    nz = None if noise is None else f64(noise)
+    nit = int(prob.nit)
+    cost = np.empty((n, 2)); status = np.zeros(n, dtype=np.int32)
+    y = np.empty((n, 2, nit)) if traj else None
+    u = np.empty((n, 2, nit)) if traj else None
+    P = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None else None
+    lib().ssnmpc_port_eval_batch(C.c_int(nit), C.c_int(int(prob.pmax)), C.c_int(int(prob.inK)), C.c_int(int(prob.nsub)),
+                                 C.c_int(int(prob.max_sqp)), C.c_double(float(prob.Ts)), P(x0), P(u0), P(lb), P(ub), P(xc), P(r), P(nz),
+                                 C.c_int(n), P(N), P(Nu), P(Qa), P(Wa), P(cost), P(y), P(u), P(status), C.c_int(int(nthreads)))
+    return (cost, status, y, u) if traj else (cost, status)
+
+
+def ssnmpc_controller(prob, x, uprev, r, N, Nu, Q, W):
+    """One NMPC_Controller call of the host build: returns (X, n_sqp, rc)."""
+    f64 = lambda a: np.ascontiguousarray(np.asarray(a, dtype=np.float64))
+    Nu = np.ascontiguousarray(Nu, dtype=np.int32); xc = np.ascontiguousarray(prob.x_control, dtype=np.int32)
+    X = np.zeros(int(Nu.sum())); ns = C.c_int(0)
+    P = lambda a: a.ctypes.data_as(C.c_void_p)
+    bufs = [f64(prob.lb), f64(prob.ub), xc, f64(x), f64(uprev), f64(r)]
+    Qa, Wa = f64(Q), f64(W)
+    rc = lib().ssnmpc_port_controller(C.c_int(int(prob.nsub)), C.c_int(int(prob.max_sqp)), C.c_double(float(prob.Ts)),
+                                      *[P(b) for b in bufs], C.c_int(int(N)), P(Nu), P(Qa), P(Wa), P(X), C.byref(ns))
+    return X, ns.value, rc
