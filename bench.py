@@ -54,7 +54,8 @@ def linear_problem(args):
 
 def metric_name(args):
     return {"shell3x3": METRIC, "shell7x5": "closed-loop tuning candidates/sec (Shell7x5, soft output bands)",
-            "dtc": "DTC-GPC sweep candidates/sec (Wood-Berry)", "vdv": "NMPC closed-loop tuning candidates/sec (Van de Vusse)"}[args.config]
+            "dtc": "DTC-GPC sweep candidates/sec (Wood-Berry)", "vdv": "NMPC closed-loop tuning candidates/sec (Van de Vusse)",
+            "ssnmpc": "single-shooting NMPC sweep candidates/sec (Explicit NMPC demo, Van de Vusse)"}[args.config]
 
 
 def workload_string(mode, pop, config="shell3x3"):
@@ -267,6 +268,10 @@ def other_workload(args):
     if args.config == "dtc":
         return (f"DTC-GPC sweep on Wood-Berry (BASELINE.json configs[3], DTC_GPC_WW.m:56-164): nit=200, population {args.pop} per GPU, "
                 "p_i~U{1..30}, m_j~U{1..min(p,10)}, delta, lambda log-uniform [1e-3,1e2], robustness filter (alfa, raio) per candidate designed on the device, PCG64 seed 0")
+    if args.config == "ssnmpc":
+        return (f"single-shooting NMPC sweep (Explicit NMPC/ClosedLoopNMPC.m:1-110, SURVEY 8f rank 4): nit=150 (147 controller calls per "
+                f"candidate), population {args.pop} per GPU, N~U{{2..12}}, Nu_j~U{{1..min(4,N)}} per input, Q log-uniform [0.1,10], "
+                "W log-uniform [1e-5,1e-2], tracking cost, PCG64 seed 0")
     return (f"Van de Vusse NMPC closed-loop evaluation (BASELINE.json configs[4], closedloop_toolbox_nmpc.m:36-97): nit=60, "
             f"population {args.pop} per GPU, N~U{{3..31}}, Nu~U{{2..15}}, delta, lambda log-uniform [1e-3,10], GAM cost, PCG64 seed 0")
 
@@ -278,6 +283,10 @@ def other_flops(args, pop):
         P, M = p.sum(axis=1), m.sum(axis=1)
         nit = 200
         return float(np.sum(2 * P * M * M + M ** 3 / 3 + 2 * P * M + nit * (2 * 2 * (P + 40) + 60)))
+    if args.config == "ssnmpc":
+        N, nz = pop[0].astype(float), pop[1].astype(float).sum(axis=1)
+        per_gn = N * 16 * 420 + N * 2 * nz * nz + nz ** 3 / 3 + 2 * N * 16 * 120    # the same convention as the other NMPC line: 3 iterations per call
+        return float(np.sum(147 * 3 * per_gn))
     N, Nu = pop[0].astype(float), pop[1].astype(float)
     nz = 2 * Nu
     per_sqp = N * 16 * 420 + N * 2 * nz * nz + nz ** 3 / 3 + 2 * N * 16 * 120     # rollout+sensitivities, H, factor, 2 cost rollouts
@@ -294,6 +303,9 @@ def run_other(args):
     if args.config == "dtc":
         prob = mpcgpu.woodberry_dtc()
         pop = mpcgpu.synthetic_dtc_population(prob, n_all, seed=0)   # (p, m, delta, lambda, alfa, raio): the robustness filter of every candidate is designed on the device
+    elif args.config == "ssnmpc":
+        prob = mpcgpu.explicit_nmpc()
+        pop = mpcgpu.synthetic_ssnmpc_population(prob, n_all, seed=0)
     else:
         prob = mpcgpu.vandevusse()
         pop = mpcgpu.synthetic_nmpc_population(prob, n_all, seed=0)
@@ -314,6 +326,12 @@ def run_other(args):
                 k += 1
             return k / (time.perf_counter() - t0), 1, k
         from oracle import nmpc_port
+        if args.config == "ssnmpc":
+            k = min(n, max(2 * nth, 16))
+            t0 = time.perf_counter(); nmpc_port.ssnmpc_eval_batch(prob, *[a[:k] for a in mine], nthreads=nth); dt = time.perf_counter() - t0
+            k = int(min(n, max(k, k * budget_s / max(dt, 1e-3))))
+            t0 = time.perf_counter(); nmpc_port.ssnmpc_eval_batch(prob, *[a[:k] for a in mine], nthreads=nth); dt = time.perf_counter() - t0
+            return k / dt, nth, k
         k = min(n, max(2 * nth, 16))
         t0 = time.perf_counter(); nmpc_port.eval_batch(prob, *[a[:k] for a in mine], "gam", nth); dt = time.perf_counter() - t0
         k = int(min(n, max(k, k * budget_s / max(dt, 1e-3))))
@@ -332,6 +350,8 @@ def run_other(args):
         sample = f"~2 s of CPU work per step on rank 0's population ({tot // max(args.steps, 1)} candidates per step)"
         kind_note = ("oracle/dtc_gpc_oracle.py: numpy restatement of DTC_GPC_WW.m, single process" if args.config == "dtc"
                      else "oracle/nmpc_port.cpp: the restated NLP + Gauss-Newton SQP on the host, OpenMP over candidates")
+        if args.config == "ssnmpc":
+            kind_note = "oracle/nmpc_port.cpp: csrc/mpc_ssnmpc_core.h (the kernel's per-run source) on the host, OpenMP over candidates"
         print(json.dumps({"impl": "reference", "metric": metric_name(args), "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
                           "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
                           "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -352,6 +372,11 @@ def run_other(args):
         call = lambda: ev.eval_batch(*mine[:4], alfa=mine[4], raio=mine[5])
         width, key = 2, "ise"
         h2d = n * (2 * 4 + 2 * 4 + 2 * 8 + 2 * 8 + 2 * 8)
+    elif args.config == "ssnmpc":
+        ev = mpcgpu.SsnmpcEvaluator(prob, device=local)
+        call = lambda: ev.eval_batch(*mine)
+        width, key = 2, "cost"
+        h2d = n * (4 + 8 + 16 + 16)
     else:
         ev = mpcgpu.NmpcEvaluator(prob, device=local)
         call = lambda: ev.eval_batch(*mine, mode="gam")
@@ -396,16 +421,17 @@ def run_other(args):
                 "clocks": clk.summary(),
                 "roofline": {"bound": "fp64_fma (serial per-run chains; neither hbm nor tensor)", "achieved": achieved, "peak": fp64_peak,
                              "unit": "TFLOP/s", "frac": achieved / fp64_peak if fp64_peak else None,
-                             "kernel": "k_dtc (warp per candidate)" if args.config == "dtc" else "k_nmpc_g<16> (sixteen lanes per run, two runs per warp, sorted by horizons)",
+                             "kernel": {"dtc": "k_dtc (warp per candidate)", "ssnmpc": "k_ssnmpc (one thread per closed loop, sorted by horizons)"}.get(
+                                 args.config, "k_nmpc_g<16> (sixteen lanes per run, two runs per warp, sorted by horizons)"),
                              "algorithmic_flops_per_launch": fl,
-                             "traffic": None if args.config == "dtc" else ncu_traffic("r2_other_kernels.json", "k_nmpc_g", (n + 1) // 2),
+                             "traffic": None if args.config in ("dtc", "ssnmpc") else ncu_traffic("r2_other_kernels.json", "k_nmpc_g", (n + 1) // 2),
                              "traffic_source": "profiles/r2_other_kernels.json (ncu --set full, same population; null otherwise)",
                              "peak_source": "mpcgpu_measure_fp64_peak, measured live"},
                 "failed_candidates": int((~ok).sum())}
         if not args.no_cpu_baseline and world == 1:
             v_, c_, k_ = cpu_rate(cores, 10.0)
             line["cpu_baseline"] = {"value": v_, "unit": UNIT, "cores": c_, "kind": "port", "sample": f"first {k_} candidates of the same population"}
-            if args.config == "vdv":
+            if args.config in ("vdv", "ssnmpc"):
                 v1, _, k1 = cpu_rate(1, 4.0)
                 line["cpu_baseline"]["single_thread"] = {"value": v1, "cores": 1, "sample": f"first {k1} candidates"}
         print(json.dumps(line), flush=True)
@@ -426,15 +452,15 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of every timed candidate")
     ap.add_argument("--parity-n", type=int, default=512, help="candidates checked against the (slow) oracle for the configurations other than the headline")
-    ap.add_argument("--config", default="shell3x3", choices=["shell3x3", "shell7x5", "dtc", "vdv"],
+    ap.add_argument("--config", default="shell3x3", choices=["shell3x3", "shell7x5", "dtc", "vdv", "ssnmpc"],
                     help="headline (BASELINE.json configs[1], default) or one of the other configurations")
     ap.add_argument("--fixed", default="", help="p,m : pin every candidate's horizons (diagnostic populations)")
     ap.add_argument("--weights", default="", help="lo,hi : log-uniform weight range (default 1e-4,10)")
     ap.add_argument("--lam", default="", help="lo,hi : override the lambda range only (diagnostics)")
     args = ap.parse_args()
     if args.pop <= 0:
-        args.pop = {"shell3x3": 4096, "shell7x5": 2048, "dtc": 16384, "vdv": 16384}[args.config]
-    if args.config in ("dtc", "vdv"):
+        args.pop = {"shell3x3": 4096, "shell7x5": 2048, "dtc": 16384, "vdv": 16384, "ssnmpc": 4096}[args.config]
+    if args.config in ("dtc", "vdv", "ssnmpc"):
         return run_other(args)
     if args.impl == "reference":
         return run_reference(args)

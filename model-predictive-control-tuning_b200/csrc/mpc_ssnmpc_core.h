@@ -44,7 +44,7 @@ NM_FN int ss_controller(const SsnmpcDev &S, const double *x0, const double *upre
     int off[NU];
     int nz = 0;
     for (int j = 0; j < NU; ++j) { off[j] = nz; nz += nuj[j]; }
-    double g[NM_MAXZ], d[NM_MAXZ], lo[NM_MAXZ], hi[NM_MAXZ], tmp[NM_MAXZ], Xt[NM_MAXZ], Sx[NX * NM_MAXZ], AB[15], bias[NY], uf[NU];
+    double g[NM_MAXZ], d[NM_MAXZ], dp[NM_MAXZ], lo[NM_MAXZ], hi[NM_MAXZ], tmp[NM_MAXZ], Xt[NM_MAXZ], Xx[NM_MAXZ], Sx[NX * NM_MAXZ], AB[15], bias[NY], uf[NU];
     int fixed[NM_MAXZ];
     {   // S3
         double xs[NX] = {x0[0], x0[1], x0[2]};
@@ -55,6 +55,7 @@ NM_FN int ss_controller(const SsnmpcDev &S, const double *x0, const double *upre
     double Jcur = ss_cost(S, x0, uprev, r, bias, p, nuj, off, Q, W, X);
     int status = 0;
     double dprev = INFINITY;
+    int prev_plain = 0;
     for (int it = 0; it < S.D.max_sqp; ++it) {
         *n_sqp += 1;
         for (int a = 0; a < nz; ++a)
@@ -99,6 +100,31 @@ NM_FN int ss_controller(const SsnmpcDev &S, const double *x0, const double *upre
         if (dmax < 1e-10) break;
         double alpha = 1.0, Jn = 0.0;
         int acc_ = 0;
+        // Gauss-Newton converges LINEARLY here after a set-point jump (large residual, W ~ 1e-4): the error contracts by a constant
+        // factor rho per full step along one direction -- measured rho ~ -0.95, the steps alternate in sign and shrink by 5 %
+        // (the Gauss-Newton Hessian underestimates the curvature there and every step overshoots to the other side).  When
+        // two successive full steps show that pattern (parallel or anti-parallel), rho = <d, d_prev> / <d_prev, d_prev> and the
+        // step that removes the mode, alpha = 1 / (1 - rho), is tried first; it is kept only if it lowers the true cost below
+        // the plain step's (it changes how fast the minimiser is reached, not which one)
+        double Jx = INFINITY, ax = 0.0;
+        if (prev_plain) {
+            double dot = 0.0, n1 = 0.0, n2 = 0.0;
+            for (int i = 0; i < nz; ++i) { dot = fma(d[i], dp[i], dot); n1 = fma(d[i], d[i], n1); n2 = fma(dp[i], dp[i], n2); }
+            const double rho = n2 > 0.0 ? dot / n2 : 0.0;
+            if (fabs(dot) > 0.95 * sqrt(n1 * n2) && fabs(rho) > 0.3 && fabs(rho) < 0.995) {
+                ax = fmin(1.0 / (1.0 - rho), 32.0);
+                for (int j = 0; j < NU; ++j)
+                    for (int c = 0; c < nuj[j]; ++c) {
+                        const int a = off[j] + c;
+                        Xx[a] = fmin(fmax(X[a] + ax * d[a], S.D.umin[j] - uprev[j]), S.D.umax[j] - uprev[j]);
+                    }
+                Jx = ss_cost(S, x0, uprev, r, bias, p, nuj, off, Q, W, Xx);
+            }
+        }
+        for (int i = 0; i < nz; ++i) dp[i] = d[i];
+#ifdef SS_DEBUG
+        printf("it %d dmax %.3e dprev %.3e ax %.2f Jx-Jcur %.3e d=[%.3e %.3e %.3e %.3e]\n", it, dmax, dprev, ax, Jx - Jcur, d[0], d[1], d[2], d[3]);
+#endif
         for (int bt = 0; bt < 6; ++bt) {
             for (int j = 0; j < NU; ++j)
                 for (int c = 0; c < nuj[j]; ++c) {
@@ -108,6 +134,11 @@ NM_FN int ss_controller(const SsnmpcDev &S, const double *x0, const double *upre
             Jn = ss_cost(S, x0, uprev, r, bias, p, nuj, off, Q, W, Xt);
             if (Jn < Jcur) { acc_ = 1; break; }
             alpha *= 0.5;
+        }
+        prev_plain = acc_ && alpha == 1.0;
+        if (Jx < Jcur && (!acc_ || Jx < Jn)) {     // the mode-removing step wins
+            for (int i = 0; i < nz; ++i) Xt[i] = Xx[i];
+            Jn = Jx; acc_ = 1; prev_plain = 0;     // no pattern to read off the step that follows it
         }
         if (!acc_) {
             // the cost no longer resolves the step (|dJ| < 1e-16 J leaves X open to ~1e-8 along the flat directions, and the
