@@ -12,7 +12,8 @@
 //   S5  u(k) = u(k-1) + X_j[0] (ClosedLoopNMPC.m:97-105); plant step, then the state perturbation noise(:,k) the caller
 //       supplies (the reference draws 0.01*randn per sample, :88-90: pass the draws to reproduce a run, nullptr for none)
 // Integrator: RK4 with nsub sub-steps where the reference uses ode23t (prediction) / ode45 (plant) -- the same stated
-// deviation as N4.  Solver: Gauss-Newton on S2 with the exact box-QP of mpc_nmpc_core.h and backtracking on the true cost,
+// deviation as N4.  Solver: Gauss-Newton on S2 with the exact box-QP of mpc_nmpc_core.h and backtracking on the true cost
+// (plus a step that removes the slowest linearly converging mode, and plain steps once the cost no longer resolves them),
 // where the reference calls fmincon-SQP (TolX 1e-6, TolFun 1e-7): the same minimiser to the tolerance stated in tests/.
 #pragma once
 #include "mpc_nmpc_core.h"
