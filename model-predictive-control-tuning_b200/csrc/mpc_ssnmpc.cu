@@ -24,36 +24,11 @@
 
 #define SS_THREADS 32
 
-struct SsArgs {
-    const int *N, *Nu;           // n, n x NU
-    const double *Q, *W;         // n x NY, n x NU
-    const double *r, *noise;     // NY x nit, NX x nit or nullptr
-    double *cost, *y, *u;        // n x NY; n x NY x nit, n x NU x nit or nullptr
-    int *status;
-    unsigned long long *counters;
-};
-
 __global__ void __launch_bounds__(SS_THREADS) k_ssnmpc(const SsnmpcDev S, int n, const int *order, SsArgs A) {
     const int item = blockIdx.x * blockDim.x + threadIdx.x;
     if (item >= n) return;
-    const int c = order[item], nit = S.D.nit;
-    const int p = A.N[c];
-    int nuj[NU], nz = 0;
-    bool ok = p >= 1 && p <= S.pmax;
-    for (int j = 0; j < NU; ++j) { nuj[j] = A.Nu[(size_t)c * NU + j]; ok = ok && nuj[j] >= 1 && nuj[j] <= p; nz += nuj[j]; }
-    if (!ok || nz > NM_MAXZ) {
-        A.status[c] = MPCGPU_CAND_INVALID;
-        for (int j = 0; j < NY; ++j) A.cost[(size_t)c * NY + j] = NAN;
-        return;
-    }
     double H[NM_LD * NM_LD], Lc[NM_LD * NM_LD];
-    unsigned n_calls = 0, n_sqp = 0;
-    const int status = ssnmpc_run(S, p, nuj, A.Q + (size_t)c * NY, A.W + (size_t)c * NU, A.r, A.noise,
-                                  A.y ? A.y + (size_t)c * NY * nit : nullptr, A.u ? A.u + (size_t)c * NU * nit : nullptr,
-                                  A.cost + (size_t)c * NY, H, Lc, &n_calls, &n_sqp);
-    A.status[c] = status;
-    atomicAdd(A.counters + 0, (unsigned long long)n_calls);
-    atomicAdd(A.counters + 1, (unsigned long long)n_sqp);
+    ss_item(S, order, A, item, H, Lc);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -191,3 +191,39 @@ NM_FN int ssnmpc_run(const SsnmpcDev &S, int p, const int *nuj, const double *Q,
     *n_calls_out = n_calls; *n_sqp_out = n_sqp;
     return status;
 }
+
+// ------------------------------------------------------------------------------------------------
+// One item of a population: what a thread of k_ssnmpc does (validation of the horizons, the run, the stores).  Shared with the
+// host build so that the indexing and the edge cases the host tests exercise are the kernel's own.
+// ------------------------------------------------------------------------------------------------
+struct SsArgs {
+    const int *N, *Nu;           // n, n x NU
+    const double *Q, *W;         // n x NY, n x NU
+    const double *r, *noise;     // NY x nit, NX x nit or nullptr
+    double *cost, *y, *u;        // n x NY; n x NY x nit, n x NU x nit or nullptr
+    int *status;
+    unsigned long long *counters;   // [0] controller calls, [1] Gauss-Newton iterations
+};
+#ifdef __CUDACC__
+#define SS_COUNT(p, v) atomicAdd((p), (unsigned long long)(v))
+#else
+#define SS_COUNT(p, v) __atomic_fetch_add((p), (unsigned long long)(v), __ATOMIC_RELAXED)
+#endif
+
+NM_FN void ss_item(const SsnmpcDev &S, const int *order, const SsArgs &A, int item, double *H, double *Lc) {
+    const int c = order ? order[item] : item, nit = S.D.nit;
+    const int p = A.N[c];
+    int nuj[NU], nz = 0;
+    bool ok = p >= 1 && p <= S.pmax;
+    for (int j = 0; j < NU; ++j) { nuj[j] = A.Nu[(size_t)c * NU + j]; ok = ok && nuj[j] >= 1 && nuj[j] <= p; nz += nuj[j]; }
+    if (!ok || nz > NM_MAXZ) {
+        A.status[c] = 4;   /* MPCGPU_CAND_INVALID */
+        if (A.cost) for (int j = 0; j < NY; ++j) A.cost[(size_t)c * NY + j] = NAN;
+        return;
+    }
+    unsigned n_calls = 0, n_sqp = 0;
+    A.status[c] = ssnmpc_run(S, p, nuj, A.Q + (size_t)c * NY, A.W + (size_t)c * NU, A.r, A.noise,
+                             A.y ? A.y + (size_t)c * NY * nit : nullptr, A.u ? A.u + (size_t)c * NU * nit : nullptr,
+                             A.cost ? A.cost + (size_t)c * NY : nullptr, H, Lc, &n_calls, &n_sqp);
+    if (A.counters) { SS_COUNT(A.counters + 0, n_calls); SS_COUNT(A.counters + 1, n_sqp); }
+}

@@ -64,7 +64,7 @@ extern "C" int nmpc_port_eval_batch(int nit, int pmax, int mmax, int inK, int ns
 extern "C" int ssnmpc_port_eval_batch(int nit, int pmax, int inK, int nsub, int max_sqp, double Ts, const double *x0, const double *u0,
                                       const double *lb, const double *ub, const int *xc, const double *r, const double *noise, int n,
                                       const int *N, const int *Nu, const double *Q, const double *W, double *cost, double *y, double *u,
-                                      int *status, int nthreads) {
+                                      int *status, int nthreads, unsigned long long *counters_out) {
     SsnmpcDev S;
     NmpcDev &D = S.D;
     D.nit = nit; D.pmax = pmax; D.mmax = NM_MAXM; D.inK = inK; D.nsub = nsub; D.max_sqp = max_sqp; D.Ts = Ts;
@@ -75,26 +75,15 @@ extern "C" int ssnmpc_port_eval_batch(int nit, int pmax, int inK, int nsub, int 
 #ifdef _OPENMP
     if (nthreads > 0) omp_set_num_threads(nthreads);
 #endif
+    unsigned long long counters[2] = {0, 0};
+    SsArgs A{N, Nu, Q, W, r, noise, cost, y, u, status, counters};
 #pragma omp parallel
     {
         std::vector<double> H(NM_LD * NM_LD), Lc(NM_LD * NM_LD);
 #pragma omp for schedule(dynamic, 1)
-        for (int c = 0; c < n; ++c) {
-            const int p = N[c], *nuj = Nu + (size_t)c * NU;
-            bool ok = p >= 1 && p <= pmax;
-            int nz = 0;
-            for (int j = 0; j < NU; ++j) { ok = ok && nuj[j] >= 1 && nuj[j] <= p; nz += nuj[j]; }
-            if (!ok || nz > NM_MAXZ) {
-                status[c] = 4;
-                if (cost) for (int j = 0; j < NY; ++j) cost[(size_t)c * NY + j] = NAN;
-                continue;
-            }
-            unsigned nc = 0, ns = 0;
-            status[c] = ssnmpc_run(S, p, nuj, Q + (size_t)c * NY, W + (size_t)c * NU, r, noise, y ? y + (size_t)c * NY * nit : nullptr,
-                                   u ? u + (size_t)c * NU * nit : nullptr, cost ? cost + (size_t)c * NY : nullptr, H.data(), Lc.data(),
-                                   &nc, &ns);
-        }
+        for (int c = 0; c < n; ++c) ss_item(S, nullptr, A, c, H.data(), Lc.data());   // what a thread of k_ssnmpc runs
     }
+    if (counters_out) { counters_out[0] = counters[0]; counters_out[1] = counters[1]; }
     return 0;
 }
 

@@ -35,7 +35,7 @@ def eval_batch(prob, N, Nu, delta, lam, mode="gam", nthreads=0):
     return cost, status
 
 
-def ssnmpc_eval_batch(prob, N, Nu, Q, W, noise=None, traj=False, nthreads=0):
+def ssnmpc_eval_batch(prob, N, Nu, Q, W, noise=None, traj=False, nthreads=0, counters=None):
     """Host build of csrc/mpc_ssnmpc_core.h (the single-shooting formulation).  prob: an SsnmpcProblem-shaped object.
     Returns (cost n x 2, status[, y, u])."""
     f64 = lambda x: np.ascontiguousarray(np.asarray(x, dtype=np.float64))
@@ -49,10 +49,13 @@ def ssnmpc_eval_batch(prob, N, Nu, Q, W, noise=None, traj=False, nthreads=0):
     cost = np.empty((n, 2)); status = np.zeros(n, dtype=np.int32)
     y = np.empty((n, 2, nit)) if traj else None
     u = np.empty((n, 2, nit)) if traj else None
+    cnt = np.zeros(2, dtype=np.uint64)
     P = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None else None
     lib().ssnmpc_port_eval_batch(C.c_int(nit), C.c_int(int(prob.pmax)), C.c_int(int(prob.inK)), C.c_int(int(prob.nsub)),
                                  C.c_int(int(prob.max_sqp)), C.c_double(float(prob.Ts)), P(x0), P(u0), P(lb), P(ub), P(xc), P(r), P(nz),
-                                 C.c_int(n), P(N), P(Nu), P(Qa), P(Wa), P(cost), P(y), P(u), P(status), C.c_int(int(nthreads)))
+                                 C.c_int(n), P(N), P(Nu), P(Qa), P(Wa), P(cost), P(y), P(u), P(status), C.c_int(int(nthreads)), P(cnt))
+    if counters is not None:
+        counters.update(controller_calls=int(cnt[0]), gn_iterations=int(cnt[1]))
     return (cost, status, y, u) if traj else (cost, status)
 
 
