@@ -93,3 +93,21 @@ def test_population_is_legal(prob):
     N, Nu, dl, lm = synthetic_nmpc_population(prob, 256, seed=0)
     assert all(prob.valid(int(a), int(b)) for a, b in zip(N, Nu))
     assert N.max() <= 31 and Nu.max() <= 15 and dl.min() >= 1e-3 and lm.max() <= 10
+
+
+def test_unenforced_bounds_are_inactive_on_the_benchmark_population():
+    """The restated NLP (N3) does not enforce the OV / state bounds of VanDeVusse_NMPC.m:140-145.  On the benchmark's own
+    seeded population no controller call's optimal plan predicts a state outside them (tools/nmpc_bounds): the unconstrained
+    optimum is feasible for nlmpc's constrained problem, so the two have the same solution in every call."""
+    import os, runpy, sys, io, contextlib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    buf = io.StringIO()
+    argv = sys.argv
+    sys.argv = ["run.py", "512"]
+    try:
+        with contextlib.redirect_stdout(buf):
+            runpy.run_path(os.path.join(root, "tools", "nmpc_bounds", "run.py"), run_name="__main__")
+    finally:
+        sys.argv = argv
+    out = buf.getvalue()
+    assert "outside its bounds: 0 (0.00%)" in out, out
