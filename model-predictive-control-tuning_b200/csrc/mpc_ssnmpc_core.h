@@ -107,13 +107,13 @@ NM_FN int ss_controller(const SsnmpcDev &S, const double *x0, const double *upre
         // two successive full steps show that pattern (parallel or anti-parallel), rho = <d, d_prev> / <d_prev, d_prev> and the
         // step that removes the mode, alpha = 1 / (1 - rho), is tried first; it is kept only if it lowers the true cost below
         // the plain step's (it changes how fast the minimiser is reached, not which one)
-        double Jx = INFINITY, ax = 0.0;
+        double Jx = INFINITY;
         if (prev_plain) {
             double dot = 0.0, n1 = 0.0, n2 = 0.0;
             for (int i = 0; i < nz; ++i) { dot = fma(d[i], dp[i], dot); n1 = fma(d[i], d[i], n1); n2 = fma(dp[i], dp[i], n2); }
             const double rho = n2 > 0.0 ? dot / n2 : 0.0;
             if (fabs(dot) > 0.95 * sqrt(n1 * n2) && fabs(rho) > 0.3 && fabs(rho) < 0.995) {
-                ax = fmin(1.0 / (1.0 - rho), 32.0);
+                const double ax = fmin(1.0 / (1.0 - rho), 32.0);
                 for (int j = 0; j < NU; ++j)
                     for (int c = 0; c < nuj[j]; ++c) {
                         const int a = off[j] + c;
@@ -123,9 +123,6 @@ NM_FN int ss_controller(const SsnmpcDev &S, const double *x0, const double *upre
             }
         }
         for (int i = 0; i < nz; ++i) dp[i] = d[i];
-#ifdef SS_DEBUG
-        printf("it %d dmax %.3e dprev %.3e ax %.2f Jx-Jcur %.3e d=[%.3e %.3e %.3e %.3e]\n", it, dmax, dprev, ax, Jx - Jcur, d[0], d[1], d[2], d[3]);
-#endif
         for (int bt = 0; bt < 6; ++bt) {
             for (int j = 0; j < NU; ++j)
                 for (int c = 0; c < nuj[j]; ++c) {
